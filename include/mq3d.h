@@ -1,0 +1,177 @@
+/*
+ * mq3d.h -- C ABI of the B200-native volumetric reconstruction hot path.
+ *
+ * This is the drop-in boundary for the Open3D calls that the reference pipeline
+ * (lszmer/metaquest-3d-reconstruction, pure Python) makes on its hot path.  Each entry point
+ * names the reference call site it replaces (paths relative to the reference's scripts/).
+ * Conventions:
+ *   - every function returns an int status (MQ3D_OK == 0); mq3d_last_error() gives the message of
+ *     the last failure on the calling thread;
+ *   - pointers named *_dev are DEVICE pointers valid on the grid's CUDA device; everything else
+ *     (camera matrices, counts) is host memory.  No torch/Open3D types appear here;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Kernels are enqueued on
+ *     it; functions documented as "synchronises" wait for that stream before returning;
+ *   - one handle <-> one CUDA device; handles are not thread-safe (the reference caller is a single
+ *     frame-sequential Python thread, processing/reconstruction/utils/o3d_utils.py:231-236);
+ *   - there is no CPU fallback: without a CUDA device every call fails with MQ3D_ERR_CUDA.
+ *
+ * Camera matrices follow the reference call sites: intrinsic K is row-major double[9], extrinsic E
+ * is row-major double[16] world->camera (o3d_utils.py:203-210), depth_scale is a float (always 1.0
+ * in the reference), block_resolution is 16.
+ */
+#ifndef MQ3D_H
+#define MQ3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ3D_OK 0
+#define MQ3D_ERR_CUDA 1             /* CUDA runtime failure (message has the cudaError string) */
+#define MQ3D_ERR_INVALID 2          /* bad argument (shape, null pointer, unsupported resolution) */
+#define MQ3D_ERR_NO_BLOCK_TOUCHED 3 /* Open3D: "No block is touched in TSDF volume ..." */
+#define MQ3D_ERR_STATE 4            /* call order violated (e.g. fill before count) */
+
+#define MQ3D_ATTR_TSDF_WEIGHT 1 /* 'tsdf','weight' float32 x1 (o3d_utils.py:171-179) */
+#define MQ3D_ATTR_COLOR 2       /* + 'color' float32 x3 (Open3D colour Integrate overload) */
+
+typedef struct mq3d_grid mq3d_grid;   /* VoxelBlockGrid state: spatial hash + block pool */
+typedef struct mq3d_scene mq3d_scene; /* RaycastingScene state: triangles + LBVH */
+
+const char *mq3d_last_error(void);
+int mq3d_version(void);
+
+/* ---- voxel block grid life cycle ------------------------------------------------------------
+ * Replaces o3d.t.geometry.VoxelBlockGrid(attr_names, attr_dtypes, attr_channels, voxel_size,
+ * block_resolution, block_count, device)            (o3d_utils.py:171-179).
+ * block_count is an initial capacity; the pool and hash grow x2 when exceeded (Open3D rehash). */
+int mq3d_grid_create(float voxel_size, int block_resolution, int64_t block_count, int attr_mask,
+                     int device, mq3d_grid **out);
+int mq3d_grid_destroy(mq3d_grid *g);
+int mq3d_grid_reset(mq3d_grid *g, void *stream);           /* drop all blocks, keep capacity */
+int mq3d_grid_reserve(mq3d_grid *g, int64_t block_count, void *stream);
+int mq3d_grid_num_blocks(mq3d_grid *g, int64_t *n, void *stream); /* synchronises */
+int mq3d_grid_info(mq3d_grid *g, float *voxel_size, int *resolution, int64_t *capacity,
+                   int *attr_mask, int *device);
+/* Raw views of the block pool (valid until the next call that may grow the pool):
+ * keys int32 [capacity][3]; tsdf/weight float32 [capacity][16][16][16] (z,y,x); color float32
+ * [capacity][16][16][16][3] or NULL.  First num_blocks entries are active.  This is the
+ * VoxelBlockGrid.save payload (dataio/reconstruction_data_io.py:51-55). */
+int mq3d_grid_pool(mq3d_grid *g, int32_t **keys_dev, float **tsdf_dev, float **weight_dev,
+                   float **color_dev);
+/* Copy the active blocks (device to device) into caller buffers sized by mq3d_grid_num_blocks:
+ * keys int32 [n][3], tsdf/weight float32 [n][4096], color float32 [n][4096][3] (NULL to skip). */
+int mq3d_grid_export(mq3d_grid *g, int32_t *keys_dev, float *tsdf_dev, float *weight_dev,
+                     float *color_dev, void *stream);
+/* VoxelBlockGrid.load (reconstruction_data_io.py:42-48): insert n blocks with their values. */
+int mq3d_grid_import(mq3d_grid *g, const int32_t *keys_dev, const float *tsdf_dev,
+                     const float *weight_dev, const float *color_dev, int64_t n, void *stream);
+/* Multi-GPU partition: this grid keeps only blocks whose super-tile
+ * (tile_blocks^3 blocks) hashes to `rank` of `world`, plus the one-block ghost shell around them.
+ * world == 1 disables filtering.  Must be called on an empty grid. */
+int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int tile_blocks);
+
+/* ---- K1: raw NDC depth -> linear metres + confidence mask -----------------------------------
+ * Replaces DepthDataIO.load_depth_map's convert_depth_to_linear + is_depth_map_valid
+ * (dataio/depth_data_io.py:33-53,80-85; utils/depth_utils.py:21-46) and the masking in
+ * o3d_utils.load_depth_map (o3d_utils.py:131-142), for n_frames frames in one launch.
+ * near/far: host double[n_frames].  conf_dev (float64) / count_dev (int32) may be NULL (no mask);
+ * has_conf_dev (uint8[n_frames], may be NULL = all present) marks frames whose confidence map
+ * exists (missing map => unfiltered depth, o3d_utils.py:137-139).
+ * frame_valid_dev int32[n_frames] receives is_depth_map_valid per frame. */
+int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width, int height, const double *near_z,
+                       const double *far_z, const double *conf_dev, const int32_t *count_dev,
+                       const uint8_t *has_conf_dev, double conf_thr, int32_t count_thr,
+                       float *out_dev, int32_t *frame_valid_dev, void *stream);
+
+/* ---- K2: frustum block activation -----------------------------------------------------------
+ * Replaces vbg.compute_unique_block_coordinates(depth, intrinsic, extrinsic, depth_scale,
+ * depth_max, trunc_voxel_multiplier) (o3d_utils.py:212-219).  Does NOT allocate blocks (Open3D
+ * uses a scratch frustum hashmap).  out_keys_dev: int32[(W/4)*(H/4)*4][3]; *out_n = number of
+ * unique keys (order unspecified).  Synchronises.  Zero touched blocks =>
+ * MQ3D_ERR_NO_BLOCK_TOUCHED (the reference's RuntimeError). */
+int mq3d_touch(mq3d_grid *g, const float *depth_dev, int width, int height, const double K[9],
+               const double E[16], float depth_scale, float depth_max, float trunc_voxel_multiplier,
+               int32_t *out_keys_dev, int64_t *out_n, void *stream);
+
+/* ---- K3: projective TSDF / weight (/ colour) update ----------------------------------------
+ * Replaces vbg.integrate(block_coords, depth, intrinsic, extrinsic, depth_scale, depth_max,
+ * trunc_voxel_multiplier) (o3d_utils.py:221-229) and Open3D's colour overload when
+ * color_dev != NULL (uint8 [CH][CW][3], colour intrinsic Kc, identity colour extrinsic).
+ * Activates the listed blocks (zero-initialised) then updates every voxel of every listed block. */
+int mq3d_integrate(mq3d_grid *g, const int32_t *keys_dev, int64_t n_keys, const float *depth_dev,
+                   int width, int height, const uint8_t *color_dev, int color_width, int color_height,
+                   const double Kd[9], const double Kc[9], const double E[16], float depth_scale,
+                   float depth_max, float trunc_voxel_multiplier, void *stream);
+
+typedef struct {
+    int64_t frames_integrated; /* frames with frame_valid != 0 */
+    int64_t block_visits;      /* sum over frames of |unique touched blocks| (Open3D's |block_coords|) */
+    int64_t blocks_loaded;     /* block residencies (one 16^3 tile load+store each) */
+    int64_t num_blocks;        /* active blocks after the call */
+    int64_t batches;
+    int64_t voxel_updates;     /* voxel visits that passed every reject (updated-voxel count) */
+} mq3d_seq_stats;
+
+/* Fused replacement of the whole per-frame loop of integrate() (o3d_utils.py:231-236):
+ * for f in frames (in order): touch -> activate -> integrate.  Frames are processed in batches of
+ * `batch_frames` (<= 256): each touched block is loaded once per batch and the frames that touched
+ * it are applied in frame order, which is bit-identical to the frame-sequential loop.
+ * depth_dev: float32 [n_frames][H][W] linear (K1 output); frame_valid_dev: int32[n_frames] or
+ * NULL; color_dev: uint8 [n_frames][CH][CW][3] or NULL; Kd/Kc: host double[n_frames][9];
+ * E: host double[n_frames][16].  Synchronises. */
+int mq3d_integrate_sequence(mq3d_grid *g, const float *depth_dev, const int32_t *frame_valid_dev,
+                            int n_frames, int width, int height, const uint8_t *color_dev,
+                            int color_width, int color_height, const double *Kd, const double *Kc,
+                            const double *E, float depth_scale, float depth_max,
+                            float trunc_voxel_multiplier, int batch_frames, mq3d_seq_stats *stats,
+                            void *stream);
+
+/* ---- K5: marching cubes / point cloud -------------------------------------------------------
+ * Replaces vbg.extract_triangle_mesh(weight_threshold, estimated_vertex_number=-1)
+ * (reconstruct_scene.py:105-108,186-189) and vbg.extract_point_cloud(weight_threshold=3.0)
+ * (reconstruct_scene.py:90).  Two calls: *_count classifies and returns sizes (synchronises);
+ * *_fill writes into caller-allocated device buffers sized by those counts.
+ * vertices/normals float32 [V][3]; triangles int32 [T][3]; vertex_keys (optional, may be NULL)
+ * int32 [V][4] = (voxel x,y,z, axis) of the lattice edge carrying the vertex.
+ * Output order is deterministic: block order, then edge/cube order inside the block. */
+int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int64_t *n_vertices,
+                            int64_t *n_triangles, void *stream);
+int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *normals_dev,
+                           int32_t *triangles_dev, int32_t *vertex_keys_dev, void *stream);
+int mq3d_extract_points_count(mq3d_grid *g, float weight_threshold, int64_t *n_points, void *stream);
+int mq3d_extract_points_fill(mq3d_grid *g, float *points_dev, float *normals_dev,
+                             int32_t *point_keys_dev, void *stream);
+
+/* ---- K4: multi-view depth confidence --------------------------------------------------------
+ * Replaces build_confidence_map over all reference frames of one side
+ * (processing/reconstruction/confidence_estimation/estimate_depth_confidences.py:15-79 and
+ * compute_pixel_error_map.py:120-220), float64 arithmetic on float32 inputs.
+ * depths_dev: float32 [N][H][W] linear; frame_valid_dev: int32[N] or NULL; K: host float[N][9]
+ * (cx already mirrored, o3d_utils.py:14-19); Ecw / Ecw_inv: host float[N][16] camera->world and its
+ * float32 inverse.  Outputs conf_dev float64 [N][H][W], count_dev int32 [N][H][W]. */
+int mq3d_confidence(const float *depths_dev, const int32_t *frame_valid_dev, int n_frames, int width,
+                    int height, const float *K, const float *Ecw, const float *Ecw_inv,
+                    int target_frame_range, double depth_max, double error_threshold,
+                    double *conf_dev, int32_t *count_dev, void *stream);
+
+/* ---- K6: colour-aligned depth raycast -------------------------------------------------------
+ * Replaces o3d.t.geometry.RaycastingScene(): add_triangles(mesh), create_rays_pinhole(K, E,
+ * width_px, height_px), cast_rays(rays)['t_hit'] (reconstruct_scene.py:197-198;
+ * o3d_utils.py:324-342).  t_hit float32 [H][W], +inf on miss, in units of the (unnormalised) ray
+ * direction, i.e. z-depth for pinhole rays. */
+int mq3d_scene_create(int device, mq3d_scene **out);
+int mq3d_scene_destroy(mq3d_scene *s);
+int mq3d_scene_add_triangles(mq3d_scene *s, const float *vertices_dev, int64_t n_vertices,
+                             const int32_t *triangles_dev, int64_t n_triangles, void *stream);
+int mq3d_scene_create_rays_pinhole(const double K[9], const double E[16], int width, int height,
+                                   float *rays_dev, void *stream);
+int mq3d_scene_cast_rays(mq3d_scene *s, const float *rays_dev, int64_t n_rays, float *t_hit_dev,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQ3D_H */

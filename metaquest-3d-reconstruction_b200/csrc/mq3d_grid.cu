@@ -1,0 +1,436 @@
+// Voxel block grid state: GPU open-addressing spatial hash + dense block pool.
+// Replaces o3d.t.geometry.VoxelBlockGrid construction / growth / save+load payload
+// (reference: processing/reconstruction/utils/o3d_utils.py:171-179,
+//  dataio/reconstruction_data_io.py:42-55).
+#include <stdarg.h>
+
+#include "mq3d_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mq3d_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *mq3d_last_error(void) { return g_err; }
+extern "C" int mq3d_version(void) { return 100; }
+
+int mq3d_set_device(int device) {
+    MQ3D_CUDA(cudaSetDevice(device));
+    return MQ3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_u64(unsigned long long *p, unsigned long long v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// re-insert every (key,val) of `src` into `dst` (dst pre-filled with EMPTY)
+__global__ void k_rehash(HashView src, int64_t src_size, HashView dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= src_size) return;
+    unsigned long long k = src.keys[i];
+    if (k == MQ3D_EMPTY_KEY) return;
+    bool fresh;
+    uint32_t s = hash_insert(dst, k, fresh);
+    dst.vals[s] = src.vals[i];
+}
+
+// block_keys[val] = unpack(key) for every occupied slot (after pool growth)
+__global__ void k_rebuild_block_keys(HashView h, int64_t size, int32_t *block_keys, int64_t capacity) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    unsigned long long k = h.keys[i];
+    if (k == MQ3D_EMPTY_KEY) return;
+    int v = h.vals[i];
+    if (v < 0 || v >= capacity) return;
+    int x, y, z;
+    mq3d_unpack_key(k, x, y, z);
+    block_keys[3 * (int64_t)v + 0] = x;
+    block_keys[3 * (int64_t)v + 1] = y;
+    block_keys[3 * (int64_t)v + 2] = z;
+}
+
+static int64_t next_pow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int alloc_table(HashView *h, int64_t size, cudaStream_t st) {
+    MQ3D_CUDA(cudaMalloc(&h->keys, sizeof(unsigned long long) * size));
+    MQ3D_CUDA(cudaMalloc(&h->vals, sizeof(int32_t) * size));
+    h->mask = (uint32_t)(size - 1);
+    k_fill_u64<<<1184, 256, 0, st>>>(h->keys, MQ3D_EMPTY_KEY, size);
+    MQ3D_CUDA(cudaMemsetAsync(h->vals, 0xFF, sizeof(int32_t) * size, st));
+    MQ3D_CUDA(cudaGetLastError());
+    return MQ3D_OK;
+}
+
+static int alloc_slot_scratch(mq3d_grid *g, cudaStream_t st) {
+    if (g->bitmap) cudaFree(g->bitmap);
+    if (g->stamp) cudaFree(g->stamp);
+    if (g->slot_list) cudaFree(g->slot_list);
+    g->bitmap_words = MQ3D_MAX_BATCH / 32;
+    MQ3D_CUDA(cudaMalloc(&g->bitmap, sizeof(uint32_t) * g->table_size * g->bitmap_words));
+    MQ3D_CUDA(cudaMalloc(&g->stamp, sizeof(int) * g->table_size));
+    MQ3D_CUDA(cudaMalloc(&g->slot_list, sizeof(int) * g->table_size));
+    MQ3D_CUDA(cudaMemsetAsync(g->bitmap, 0, sizeof(uint32_t) * g->table_size * g->bitmap_words, st));
+    MQ3D_CUDA(cudaMemsetAsync(g->stamp, 0, sizeof(int) * g->table_size, st));
+    return MQ3D_OK;
+}
+
+static int alloc_pool(mq3d_grid *g, int64_t cap, int32_t **keys, float **tsdf, float **weight, float **color,
+                      cudaStream_t st) {
+    MQ3D_CUDA(cudaMalloc(keys, sizeof(int32_t) * 3 * cap));
+    MQ3D_CUDA(cudaMalloc(tsdf, sizeof(float) * MQ3D_RES3 * cap));
+    MQ3D_CUDA(cudaMalloc(weight, sizeof(float) * MQ3D_RES3 * cap));
+    *color = nullptr;
+    if (g->attr_mask & MQ3D_ATTR_COLOR) MQ3D_CUDA(cudaMalloc(color, sizeof(float) * 3 * MQ3D_RES3 * cap));
+    (void)st;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t block_count, int attr_mask,
+                                int device, mq3d_grid **out) {
+    MQ3D_REQUIRE(out != nullptr, "null output handle");
+    MQ3D_REQUIRE(block_resolution == MQ3D_RES, "only block_resolution == 16 is supported");
+    MQ3D_REQUIRE(voxel_size > 0.0f, "voxel_size must be positive");
+    MQ3D_REQUIRE(block_count > 0, "block_count must be positive");
+    MQ3D_REQUIRE(attr_mask & MQ3D_ATTR_TSDF_WEIGHT, "tsdf/weight attributes are required");
+    int n_dev = 0;
+    MQ3D_CUDA(cudaGetDeviceCount(&n_dev));
+    MQ3D_REQUIRE(device >= 0 && device < n_dev, "CUDA device not available (no CPU fallback)");
+    MQ3D_TRY(mq3d_set_device(device));
+    mq3d_grid *g = new mq3d_grid();
+    memset(g, 0, sizeof(*g));
+    g->voxel_size = voxel_size;
+    g->attr_mask = attr_mask;
+    g->device = device;
+    g->part.rank = 0;
+    g->part.world = 1;
+    g->part.tile_shift = 3;
+    g->capacity = block_count;
+    g->table_size = next_pow2(block_count * 2 < 1024 ? 1024 : block_count * 2);
+    cudaStream_t st = 0;
+    int rc = alloc_table(&g->hash, g->table_size, st);
+    if (rc == MQ3D_OK) rc = alloc_pool(g, g->capacity, &g->block_keys, &g->tsdf, &g->weight, &g->color, st);
+    if (rc == MQ3D_OK) {
+        rc = [&]() -> int {
+            MQ3D_CUDA(cudaMemsetAsync(g->tsdf, 0, sizeof(float) * MQ3D_RES3 * g->capacity, st));
+            MQ3D_CUDA(cudaMemsetAsync(g->weight, 0, sizeof(float) * MQ3D_RES3 * g->capacity, st));
+            if (g->color) MQ3D_CUDA(cudaMemsetAsync(g->color, 0, sizeof(float) * 3 * MQ3D_RES3 * g->capacity, st));
+            MQ3D_CUDA(cudaMalloc(&g->n_blocks_dev, sizeof(int)));
+            MQ3D_CUDA(cudaMemsetAsync(g->n_blocks_dev, 0, sizeof(int), st));
+            MQ3D_CUDA(cudaMalloc(&g->counter_dev, sizeof(int) * 8));
+            MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * 8, st));
+            MQ3D_CUDA(cudaMalloc(&g->frame_params_dev, sizeof(FrameParams) * MQ3D_MAX_BATCH));
+            MQ3D_CUDA(cudaMallocHost(&g->pinned_host, sizeof(int) * 8));
+            return MQ3D_OK;
+        }();
+    }
+    if (rc == MQ3D_OK) rc = alloc_slot_scratch(g, st);
+    if (rc == MQ3D_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            mq3d_set_error("grid_create sync: %s", cudaGetErrorString(e));
+            rc = MQ3D_ERR_CUDA;
+        }
+    }
+    if (rc != MQ3D_OK) {
+        mq3d_grid_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return MQ3D_OK;
+}
+
+static void free_mc(mq3d_grid *g) {
+    cudaFree(g->mc_nb);
+    cudaFree(g->mc_emask);
+    cudaFree(g->mc_eprefix);
+    cudaFree(g->mc_cubes);
+    cudaFree(g->mc_counts);
+    cudaFree(g->mc_offsets);
+    g->mc_nb = nullptr;
+    g->mc_emask = nullptr;
+    g->mc_eprefix = nullptr;
+    g->mc_cubes = nullptr;
+    g->mc_counts = nullptr;
+    g->mc_offsets = nullptr;
+    g->mc_alloc_blocks = 0;
+    g->mc_state = 0;
+}
+
+extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
+    if (!g) return MQ3D_OK;
+    cudaSetDevice(g->device);
+    cudaFree(g->hash.keys);
+    cudaFree(g->hash.vals);
+    cudaFree(g->frustum.keys);
+    cudaFree(g->frustum.vals);
+    cudaFree(g->block_keys);
+    cudaFree(g->tsdf);
+    cudaFree(g->weight);
+    cudaFree(g->color);
+    cudaFree(g->n_blocks_dev);
+    cudaFree(g->counter_dev);
+    cudaFree(g->bitmap);
+    cudaFree(g->stamp);
+    cudaFree(g->slot_list);
+    cudaFree(g->frame_params_dev);
+    cudaFree(g->idx_scratch);
+    if (g->pinned_host) cudaFreeHost(g->pinned_host);
+    free_mc(g);
+    delete g;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_info(mq3d_grid *g, float *voxel_size, int *resolution, int64_t *capacity,
+                              int *attr_mask, int *device) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    if (voxel_size) *voxel_size = g->voxel_size;
+    if (resolution) *resolution = MQ3D_RES;
+    if (capacity) *capacity = g->capacity;
+    if (attr_mask) *attr_mask = g->attr_mask;
+    if (device) *device = g->device;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int tile_blocks) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    int shift = 0;
+    while ((1 << shift) < tile_blocks) ++shift;
+    MQ3D_REQUIRE((1 << shift) == tile_blocks && tile_blocks >= 1, "tile_blocks must be a power of two");
+    MQ3D_REQUIRE(g->n_blocks_host == 0, "partition must be set on an empty grid");
+    g->part.rank = rank;
+    g->part.world = world;
+    g->part.tile_shift = shift;
+    return MQ3D_OK;
+}
+
+int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st) {
+    MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host, g->n_blocks_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MQ3D_CUDA(cudaStreamSynchronize(st));
+    g->n_blocks_host = g->pinned_host[0];
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_num_blocks(mq3d_grid *g, int64_t *n, void *stream) {
+    MQ3D_REQUIRE(g != nullptr && n != nullptr, "null argument");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    MQ3D_TRY(mq3d_grid_sync_count(g, as_stream(stream)));
+    *n = g->n_blocks_host;
+    return MQ3D_OK;
+}
+
+// Grow pool (and table) so that `need` blocks fit.  n_blocks_host must be current.
+int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool *rehashed) {
+    if (rehashed) *rehashed = false;
+    if (need > g->capacity) {
+        int64_t new_cap = g->capacity * 2;
+        while (new_cap < need) new_cap *= 2;
+        int32_t *nk;
+        float *nt, *nw, *nc;
+        MQ3D_TRY(alloc_pool(g, new_cap, &nk, &nt, &nw, &nc, st));
+        int64_t live = g->n_blocks_host < g->capacity ? g->n_blocks_host : g->capacity;
+        MQ3D_CUDA(cudaMemcpyAsync(nt, g->tsdf, sizeof(float) * MQ3D_RES3 * live, cudaMemcpyDeviceToDevice, st));
+        MQ3D_CUDA(cudaMemcpyAsync(nw, g->weight, sizeof(float) * MQ3D_RES3 * live, cudaMemcpyDeviceToDevice, st));
+        MQ3D_CUDA(cudaMemsetAsync(nt + MQ3D_RES3 * live, 0, sizeof(float) * MQ3D_RES3 * (new_cap - live), st));
+        MQ3D_CUDA(cudaMemsetAsync(nw + MQ3D_RES3 * live, 0, sizeof(float) * MQ3D_RES3 * (new_cap - live), st));
+        if (nc) {
+            MQ3D_CUDA(cudaMemcpyAsync(nc, g->color, sizeof(float) * 3 * MQ3D_RES3 * live, cudaMemcpyDeviceToDevice, st));
+            MQ3D_CUDA(cudaMemsetAsync(nc + 3 * MQ3D_RES3 * live, 0, sizeof(float) * 3 * MQ3D_RES3 * (new_cap - live), st));
+        }
+        MQ3D_CUDA(cudaStreamSynchronize(st));
+        cudaFree(g->block_keys);
+        cudaFree(g->tsdf);
+        cudaFree(g->weight);
+        cudaFree(g->color);
+        g->block_keys = nk;
+        g->tsdf = nt;
+        g->weight = nw;
+        g->color = nc;
+        g->capacity = new_cap;
+        int64_t grid = (g->table_size + 255) / 256;
+        k_rebuild_block_keys<<<(unsigned)grid, 256, 0, st>>>(g->hash, g->table_size, g->block_keys, g->capacity);
+        MQ3D_CUDA(cudaGetLastError());
+        g->mc_state = 0;
+    }
+    if (need * 2 > g->table_size) {
+        int64_t new_size = g->table_size;
+        while (need * 2 > new_size) new_size *= 2;
+        HashView nh;
+        MQ3D_TRY(alloc_table(&nh, new_size, st));
+        int64_t grid = (g->table_size + 255) / 256;
+        k_rehash<<<(unsigned)grid, 256, 0, st>>>(g->hash, g->table_size, nh);
+        MQ3D_CUDA(cudaGetLastError());
+        MQ3D_CUDA(cudaStreamSynchronize(st));
+        cudaFree(g->hash.keys);
+        cudaFree(g->hash.vals);
+        g->hash = nh;
+        g->table_size = new_size;
+        MQ3D_TRY(alloc_slot_scratch(g, st));
+        if (rehashed) *rehashed = true;
+    }
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_reserve(mq3d_grid *g, int64_t block_count, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    MQ3D_TRY(mq3d_grid_sync_count(g, as_stream(stream)));
+    return mq3d_grid_ensure_capacity(g, block_count, as_stream(stream), nullptr);
+}
+
+extern "C" int mq3d_grid_reset(mq3d_grid *g, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    int64_t live = g->n_blocks_host < g->capacity ? g->n_blocks_host : g->capacity;
+    k_fill_u64<<<1184, 256, 0, st>>>(g->hash.keys, MQ3D_EMPTY_KEY, g->table_size);
+    MQ3D_CUDA(cudaMemsetAsync(g->hash.vals, 0xFF, sizeof(int32_t) * g->table_size, st));
+    MQ3D_CUDA(cudaMemsetAsync(g->tsdf, 0, sizeof(float) * MQ3D_RES3 * live, st));
+    MQ3D_CUDA(cudaMemsetAsync(g->weight, 0, sizeof(float) * MQ3D_RES3 * live, st));
+    if (g->color) MQ3D_CUDA(cudaMemsetAsync(g->color, 0, sizeof(float) * 3 * MQ3D_RES3 * live, st));
+    MQ3D_CUDA(cudaMemsetAsync(g->n_blocks_dev, 0, sizeof(int), st));
+    MQ3D_CUDA(cudaMemsetAsync(g->bitmap, 0, sizeof(uint32_t) * g->table_size * g->bitmap_words, st));
+    MQ3D_CUDA(cudaMemsetAsync(g->stamp, 0, sizeof(int) * g->table_size, st));
+    MQ3D_CUDA(cudaStreamSynchronize(st));
+    g->n_blocks_host = 0;
+    g->batch_serial = 0;
+    g->mc_state = 0;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_pool(mq3d_grid *g, int32_t **keys_dev, float **tsdf_dev, float **weight_dev,
+                              float **color_dev) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    if (keys_dev) *keys_dev = g->block_keys;
+    if (tsdf_dev) *tsdf_dev = g->tsdf;
+    if (weight_dev) *weight_dev = g->weight;
+    if (color_dev) *color_dev = g->color;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_export(mq3d_grid *g, int32_t *keys_dev, float *tsdf_dev, float *weight_dev,
+                                float *color_dev, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    int64_t n = g->n_blocks_host;
+    if (n == 0) return MQ3D_OK;
+    const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+    if (keys_dev) MQ3D_CUDA(cudaMemcpyAsync(keys_dev, g->block_keys, sizeof(int32_t) * 3 * n, d2d, st));
+    if (tsdf_dev) MQ3D_CUDA(cudaMemcpyAsync(tsdf_dev, g->tsdf, sizeof(float) * MQ3D_RES3 * n, d2d, st));
+    if (weight_dev) MQ3D_CUDA(cudaMemcpyAsync(weight_dev, g->weight, sizeof(float) * MQ3D_RES3 * n, d2d, st));
+    if (color_dev && g->color) MQ3D_CUDA(cudaMemcpyAsync(color_dev, g->color, sizeof(float) * 3 * MQ3D_RES3 * n, d2d, st));
+    MQ3D_CUDA(cudaStreamSynchronize(st));
+    return MQ3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation of explicit key lists (per-frame integrate, import)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int *n_blocks, int32_t *block_keys,
+                                int64_t capacity, Partition part, int *bad_key_flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
+    if (!mq3d_key_in_range(x, y, z)) {
+        *bad_key_flag = 1;
+        return;
+    }
+    if (!mq3d_block_needed(x, y, z, part)) return;
+    bool fresh;
+    uint32_t s = hash_insert(h, mq3d_pack_key(x, y, z), fresh);
+    if (fresh) {
+        int b = atomicAdd(n_blocks, 1);
+        h.vals[s] = b;
+        if (b < capacity) {
+            block_keys[3 * (int64_t)b] = x;
+            block_keys[3 * (int64_t)b + 1] = y;
+            block_keys[3 * (int64_t)b + 2] = z;
+        }
+    }
+}
+
+__global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, int32_t *idx_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
+    int32_t r = -1;
+    if (mq3d_key_in_range(x, y, z)) {
+        uint32_t s = hash_find(h, mq3d_pack_key(x, y, z));
+        if (s != 0xFFFFFFFFu) r = h.vals[s];
+    }
+    idx_out[i] = r;
+}
+
+// Activate + Find (Open3D Integrate preamble).  Leaves block indices in g->idx_scratch.
+int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, cudaStream_t st) {
+    if (n > g->idx_scratch_size) {
+        cudaFree(g->idx_scratch);
+        g->idx_scratch = nullptr;
+        int64_t sz = next_pow2(n);
+        MQ3D_CUDA(cudaMalloc(&g->idx_scratch, sizeof(int32_t) * sz));
+        g->idx_scratch_size = sz;
+    }
+    // worst case every key is new: make room first so indices never exceed the pool
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    bool rehashed;
+    MQ3D_TRY(mq3d_grid_ensure_capacity(g, g->n_blocks_host + n, st, &rehashed));
+    MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int), st));
+    unsigned grid = (unsigned)((n + 255) / 256);
+    k_activate_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->n_blocks_dev, g->block_keys, g->capacity,
+                                          g->part, g->counter_dev);
+    k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->idx_scratch);
+    MQ3D_CUDA(cudaGetLastError());
+    g->mc_state = 0;
+    return MQ3D_OK;
+}
+
+__global__ void k_import_values(const int32_t *idx, int64_t n, const float *src_t, const float *src_w,
+                                const float *src_c, float *tsdf, float *weight, float *color) {
+    int64_t i = blockIdx.x;
+    if (i >= n) return;
+    int b = idx[i];
+    if (b < 0) return;
+    const float4 *st4 = reinterpret_cast<const float4 *>(src_t + i * MQ3D_RES3);
+    const float4 *sw4 = reinterpret_cast<const float4 *>(src_w + i * MQ3D_RES3);
+    float4 *dt4 = reinterpret_cast<float4 *>(tsdf + (int64_t)b * MQ3D_RES3);
+    float4 *dw4 = reinterpret_cast<float4 *>(weight + (int64_t)b * MQ3D_RES3);
+    for (int k = threadIdx.x; k < MQ3D_RES3 / 4; k += blockDim.x) {
+        dt4[k] = st4[k];
+        dw4[k] = sw4[k];
+    }
+    if (color && src_c) {
+        const float4 *sc4 = reinterpret_cast<const float4 *>(src_c + i * 3 * MQ3D_RES3);
+        float4 *dc4 = reinterpret_cast<float4 *>(color + (int64_t)b * 3 * MQ3D_RES3);
+        for (int k = threadIdx.x; k < 3 * MQ3D_RES3 / 4; k += blockDim.x) dc4[k] = sc4[k];
+    }
+}
+
+extern "C" int mq3d_grid_import(mq3d_grid *g, const int32_t *keys_dev, const float *tsdf_dev,
+                                const float *weight_dev, const float *color_dev, int64_t n, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_REQUIRE(n >= 0, "negative block count");
+    if (n == 0) return MQ3D_OK;
+    MQ3D_REQUIRE(keys_dev && tsdf_dev && weight_dev, "null block arrays");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    MQ3D_TRY(mq3d_grid_activate(g, keys_dev, n, st));
+    k_import_values<<<(unsigned)n, 256, 0, st>>>(g->idx_scratch, n, tsdf_dev, weight_dev, color_dev, g->tsdf,
+                                                  g->weight, g->color);
+    MQ3D_CUDA(cudaGetLastError());
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    return MQ3D_OK;
+}

@@ -1,0 +1,384 @@
+"""VoxelBlockGrid: the host-side mirror of ``o3d.t.geometry.VoxelBlockGrid`` for the hot path.
+
+Same call shapes as the reference's call sites (processing/reconstruction/utils/o3d_utils.py:171-229,
+processing/reconstruction/reconstruct_scene.py:87-108,186-189, dataio/reconstruction_data_io.py:42-55),
+backed by the C ABI in include/mq3d.h.  Buffers are torch CUDA tensors (device memory + streams
+only); all arithmetic happens in libmq3d.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+RES = 16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_np(x, dtype, shape=None):
+    if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+        x = x.cpu().numpy() if hasattr(x, "cpu") else x.numpy()
+    a = np.ascontiguousarray(np.asarray(x), dtype=dtype)
+    if shape is not None and a.shape != shape:
+        raise RuntimeError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _device_index(device) -> int:
+    if isinstance(device, int):
+        return device
+    if isinstance(device, torch.device):
+        if device.type != "cuda":
+            raise RuntimeError(f"device {device} is not a CUDA device; this build has no CPU fallback")
+        return device.index if device.index is not None else torch.cuda.current_device()
+    s = str(device).upper()
+    if s.startswith("CUDA"):
+        return int(s.split(":")[1]) if ":" in s else 0
+    raise RuntimeError(f"device '{device}' is not a CUDA device; this build has no CPU fallback")
+
+
+def as_depth_tensor(depth, device: torch.device) -> torch.Tensor:
+    """float32 [H,W] (or [H,W,1]) depth on the grid's device."""
+    if hasattr(depth, "as_tensor"):
+        depth = depth.as_tensor()
+    if hasattr(depth, "torch"):
+        depth = depth.torch
+    if isinstance(depth, np.ndarray):
+        depth = torch.from_numpy(np.ascontiguousarray(depth))
+    if not isinstance(depth, torch.Tensor):
+        raise RuntimeError("depth must be an Image, a Tensor, a numpy array or a torch tensor")
+    if depth.dim() == 3 and depth.shape[-1] == 1:
+        depth = depth[..., 0]
+    if depth.dim() != 2:
+        raise RuntimeError(f"depth must be [H,W] or [H,W,1], got {tuple(depth.shape)}")
+    if depth.dtype != torch.float32:
+        raise RuntimeError(f"depth must be float32, got {depth.dtype}")
+    return depth.to(device, non_blocking=True).contiguous()
+
+
+@dataclass
+class SequenceStats:
+    frames_integrated: int
+    block_visits: int
+    blocks_loaded: int
+    num_blocks: int
+    batches: int
+    voxel_updates: int
+
+    @property
+    def voxel_visits(self) -> int:
+        return self.block_visits * RES ** 3
+
+
+class VoxelBlockGrid:
+    """GPU spatial hash + block pool with Open3D-0.19 VoxelBlockGrid semantics."""
+
+    def __init__(self, attr_names: Sequence[str] = ("tsdf", "weight"), attr_dtypes=None, attr_channels=None,
+                 voxel_size: float = 0.0058, block_resolution: int = 16, block_count: int = 10000,
+                 device="CUDA:0"):
+        names = tuple(attr_names)
+        if names[:2] != ("tsdf", "weight") or any(n not in ("tsdf", "weight", "color") for n in names):
+            raise RuntimeError(f"unsupported attributes {names}: expected ('tsdf','weight'[, 'color'])")
+        if attr_channels is not None:
+            ch = tuple(int(np.prod(c)) for c in attr_channels)
+            want = (1, 1, 3)[: len(names)]
+            if ch != want:
+                raise RuntimeError(f"attr_channels {ch} do not match {want}")
+        self.attr_names = names
+        self.voxel_size = float(voxel_size)
+        self.block_resolution = int(block_resolution)
+        self.device_index = _device_index(device)
+        self.device = torch.device("cuda", self.device_index)
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available; the B200 path has no CPU fallback")
+        mask = _lib.ATTR_TSDF_WEIGHT | (_lib.ATTR_COLOR if "color" in names else 0)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_create(C.c_float(voxel_size), self.block_resolution, int(block_count),
+                                                   mask, self.device_index, C.byref(h)))
+        self._h = h
+        self._keys_scratch: Optional[torch.Tensor] = None
+
+    # -- life cycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().mq3d_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def has_color(self) -> bool:
+        return "color" in self.attr_names
+
+    def num_blocks(self) -> int:
+        n = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_num_blocks(self._h, C.byref(n), _stream()))
+        return int(n.value)
+
+    def capacity(self) -> int:
+        cap = C.c_int64()
+        _lib.check(_lib.lib().mq3d_grid_info(self._h, None, None, C.byref(cap), None, None))
+        return int(cap.value)
+
+    def reserve(self, block_count: int):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_reserve(self._h, int(block_count), _stream()))
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_reset(self._h, _stream()))
+
+    def set_partition(self, rank: int, world: int, tile_blocks: int = 8):
+        _lib.check(_lib.lib().mq3d_grid_set_partition(self._h, int(rank), int(world), int(tile_blocks)))
+
+    # -- K2 -----------------------------------------------------------------------------------------
+    def compute_unique_block_coordinates(self, depth, intrinsic, extrinsic, depth_scale: float = 1000.0,
+                                         depth_max: float = 3.0, trunc_voxel_multiplier: float = 8.0) -> torch.Tensor:
+        """int32 [N,3] block keys touched by the frame (order unspecified); does not allocate."""
+        d = as_depth_tensor(depth, self.device)
+        H, W = d.shape
+        K = _as_np(intrinsic, np.float64, (3, 3))
+        E = _as_np(extrinsic, np.float64, (4, 4))
+        cap = (W // 4) * (H // 4) * 4
+        if self._keys_scratch is None or self._keys_scratch.shape[0] < cap:
+            self._keys_scratch = torch.empty((cap, 3), dtype=torch.int32, device=self.device)
+        n = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_touch(self._h, _lib.dptr(d), W, H, _lib.darr(K), _lib.darr(E),
+                                             C.c_float(depth_scale), C.c_float(depth_max),
+                                             C.c_float(trunc_voxel_multiplier), _lib.dptr(self._keys_scratch),
+                                             C.byref(n), _stream()))
+        return self._keys_scratch[: n.value].clone()
+
+    # -- K3 -----------------------------------------------------------------------------------------
+    def integrate(self, block_coords, depth, *args, **kwargs):
+        """Open3D overloads:
+        integrate(block_coords, depth, intrinsic, extrinsic, depth_scale, depth_max, trunc_voxel_multiplier)
+        integrate(block_coords, depth, color, depth_intrinsic, color_intrinsic, extrinsic, depth_scale, ...)
+        """
+        names_d = ["intrinsic", "extrinsic", "depth_scale", "depth_max", "trunc_voxel_multiplier"]
+        names_c = ["color", "depth_intrinsic", "color_intrinsic", "extrinsic", "depth_scale", "depth_max",
+                   "trunc_voxel_multiplier"]
+        with_color = "color" in kwargs or len(args) >= 4 and not np.isscalar(args[2])
+        names = names_c if with_color else names_d
+        p = dict(zip(names, args))
+        p.update(kwargs)
+        depth_scale = float(p.get("depth_scale", 1000.0))
+        depth_max = float(p.get("depth_max", 3.0))
+        trunc = float(p.get("trunc_voxel_multiplier", 8.0))
+        Kd = _as_np(p["depth_intrinsic"] if with_color else p["intrinsic"], np.float64, (3, 3))
+        E = _as_np(p["extrinsic"], np.float64, (4, 4))
+        d = as_depth_tensor(depth, self.device)
+        H, W = d.shape
+        keys = block_coords.torch if hasattr(block_coords, "torch") else block_coords
+        if isinstance(keys, np.ndarray):
+            keys = torch.from_numpy(np.ascontiguousarray(keys, dtype=np.int32))
+        keys = keys.to(self.device).to(torch.int32).contiguous()
+        if keys.dim() != 2 or keys.shape[1] != 3:
+            raise RuntimeError(f"block_coords must be [N,3], got {tuple(keys.shape)}")
+        col, Kc, CW, CH = None, Kd, 0, 0
+        if with_color and self.has_color:
+            col = p["color"]
+            col = col.as_tensor() if hasattr(col, "as_tensor") else col
+            col = col.torch if hasattr(col, "torch") else col
+            if isinstance(col, np.ndarray):
+                col = torch.from_numpy(np.ascontiguousarray(col))
+            if col.dtype != torch.uint8 or col.dim() != 3 or col.shape[2] != 3:
+                raise RuntimeError("color must be uint8 [H,W,3]")
+            col = col.to(self.device).contiguous()
+            CH, CW = int(col.shape[0]), int(col.shape[1])
+            Kc = _as_np(p["color_intrinsic"], np.float64, (3, 3))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_integrate(self._h, _lib.dptr(keys), int(keys.shape[0]), _lib.dptr(d), W, H,
+                                                 _lib.dptr(col), CW, CH, _lib.darr(Kd), _lib.darr(Kc), _lib.darr(E),
+                                                 C.c_float(depth_scale), C.c_float(depth_max), C.c_float(trunc),
+                                                 _stream()))
+
+    def integrate_sequence(self, depths: torch.Tensor, intrinsics, extrinsics, depth_max: float,
+                           trunc_voxel_multiplier: float, depth_scale: float = 1.0,
+                           frame_valid: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
+                           color_intrinsics=None, batch_frames: int = 64) -> SequenceStats:
+        """Fused frame loop of ``integrate()`` (o3d_utils.py:231-236) over [F,H,W] linear depth."""
+        if depths.dim() != 3 or depths.dtype != torch.float32 or not depths.is_cuda:
+            raise RuntimeError("depths must be a float32 CUDA tensor [F,H,W]")
+        depths = depths.contiguous()
+        F, H, W = depths.shape
+        Kd = _as_np(intrinsics, np.float64, (F, 3, 3))
+        E = _as_np(extrinsics, np.float64, (F, 4, 4))
+        fv = None
+        if frame_valid is not None:
+            fv = frame_valid.to(self.device).to(torch.int32).contiguous()
+        col, Kc, CW, CH = None, Kd, 0, 0
+        if colors is not None and self.has_color:
+            if colors.dtype != torch.uint8 or colors.dim() != 4 or colors.shape[0] != F or colors.shape[3] != 3:
+                raise RuntimeError("colors must be uint8 [F,H,W,3]")
+            col = colors.to(self.device).contiguous()
+            CH, CW = int(col.shape[1]), int(col.shape[2])
+            Kc = _as_np(color_intrinsics, np.float64, (F, 3, 3))
+        st = _lib.SeqStats()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_integrate_sequence(
+                self._h, _lib.dptr(depths), _lib.dptr(fv), F, W, H, _lib.dptr(col), CW, CH, _lib.darr(Kd),
+                _lib.darr(Kc), _lib.darr(E), C.c_float(depth_scale), C.c_float(depth_max),
+                C.c_float(trunc_voxel_multiplier), int(batch_frames), C.byref(st), _stream()))
+        return SequenceStats(st.frames_integrated, st.block_visits, st.blocks_loaded, st.num_blocks, st.batches,
+                             st.voxel_updates)
+
+    # -- pool views / persistence -------------------------------------------------------------------
+    def _pool_ptrs(self):
+        k, t, w, c = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().mq3d_grid_pool(self._h, C.byref(k), C.byref(t), C.byref(w), C.byref(c)))
+        return k.value, t.value, w.value, c.value
+
+    def export_blocks(self):
+        """(keys int32 [N,3], tsdf f32 [N,16,16,16], weight f32 [N,16,16,16], color f32 [N,16,16,16,3]|None)
+        as torch CUDA tensors (copies of the active part of the pool)."""
+        n = self.num_blocks()
+        keys = torch.empty((n, 3), dtype=torch.int32, device=self.device)
+        tsdf = torch.empty((n, RES, RES, RES), dtype=torch.float32, device=self.device)
+        weight = torch.empty_like(tsdf)
+        color = torch.empty((n, RES, RES, RES, 3), dtype=torch.float32, device=self.device) if self.has_color else None
+        if n:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().mq3d_grid_export(self._h, _lib.dptr(keys), _lib.dptr(tsdf), _lib.dptr(weight),
+                                                       _lib.dptr(color), _stream()))
+        return keys, tsdf, weight, color
+
+    def import_blocks(self, keys, tsdf, weight, color=None):
+        def dev(x, dt):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            return x.to(self.device).to(dt).contiguous()
+        keys, tsdf, weight = dev(keys, torch.int32), dev(tsdf, torch.float32), dev(weight, torch.float32)
+        color = dev(color, torch.float32) if self.has_color else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_import(self._h, _lib.dptr(keys), _lib.dptr(tsdf), _lib.dptr(weight),
+                                                   _lib.dptr(color), int(keys.shape[0]), _stream()))
+            torch.cuda.current_stream().synchronize()
+
+    def save(self, path: str):
+        """Open3D VoxelBlockGrid.save npz layout (reconstruction_data_io.py:51-55)."""
+        keys, tsdf, weight, color = self.export_blocks()
+        out = {
+            "voxel_size": np.array([self.voxel_size], dtype=np.float32),
+            "block_resolution": np.array([self.block_resolution], dtype=np.int64),
+            f"CUDA:{self.device_index}": np.zeros((), dtype=np.uint8),
+            "key": keys.cpu().numpy(),
+        }
+        vals = [tsdf.cpu().numpy()[..., None], weight.cpu().numpy()[..., None]]
+        if color is not None:
+            vals.append(color.cpu().numpy())
+        for i, (name, v) in enumerate(zip(self.attr_names, vals)):
+            out[f"attr_name_{name}"] = np.array([i], dtype=np.int32)
+            out[f"value_{i:03d}"] = v
+        path = str(path)
+        np.savez(path if path.endswith(".npz") else path + ".npz", **out)
+
+    @classmethod
+    def load(cls, path: str, device="CUDA:0") -> "VoxelBlockGrid":
+        z = np.load(str(path))
+        names = sorted((k[len("attr_name_"):] for k in z.files if k.startswith("attr_name_")),
+                       key=lambda n: int(z[f"attr_name_{n}"][0]))
+        keys = z["key"]
+        g = cls(attr_names=tuple(names), voxel_size=float(z["voxel_size"][0]),
+                block_resolution=int(z["block_resolution"][0]), block_count=max(len(keys), 16), device=device)
+        vals = {n: z[f"value_{int(z[f'attr_name_{n}'][0]):03d}"] for n in names}
+        g.import_blocks(keys, vals["tsdf"][..., 0], vals["weight"][..., 0], vals.get("color"))
+        return g
+
+    # -- K5 -----------------------------------------------------------------------------------------
+    def extract_triangle_mesh_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False):
+        """(vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, vertex_keys i32 [V,4]]) on device."""
+        V, T = C.c_int64(), C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_extract_mesh_count(self._h, C.c_float(weight_threshold), C.byref(V),
+                                                          C.byref(T), _stream()))
+            verts = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
+            normals = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
+            tris = torch.empty((T.value, 3), dtype=torch.int32, device=self.device)
+            vkeys = torch.empty((V.value, 4), dtype=torch.int32, device=self.device) if with_keys else None
+            _lib.check(_lib.lib().mq3d_extract_mesh_fill(self._h, _lib.dptr(verts), _lib.dptr(normals),
+                                                         _lib.dptr(tris), _lib.dptr(vkeys), _stream()))
+        return (verts, normals, tris, vkeys) if with_keys else (verts, normals, tris)
+
+    def extract_point_cloud_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False):
+        P = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_extract_points_count(self._h, C.c_float(weight_threshold), C.byref(P), _stream()))
+            pts = torch.empty((P.value, 3), dtype=torch.float32, device=self.device)
+            nrm = torch.empty((P.value, 3), dtype=torch.float32, device=self.device)
+            pk = torch.empty((P.value, 4), dtype=torch.int32, device=self.device) if with_keys else None
+            _lib.check(_lib.lib().mq3d_extract_points_fill(self._h, _lib.dptr(pts), _lib.dptr(nrm), _lib.dptr(pk),
+                                                           _stream()))
+        return (pts, nrm, pk) if with_keys else (pts, nrm)
+
+    def extract_triangle_mesh(self, weight_threshold: float = 3.0, estimated_vertex_number: int = -1):
+        from .geometry import TriangleMesh
+        v, n, t = self.extract_triangle_mesh_arrays(weight_threshold)
+        return TriangleMesh(v, t, n)
+
+    def extract_point_cloud(self, weight_threshold: float = 3.0, estimated_point_number: int = -1):
+        from .geometry import PointCloud
+        p, n = self.extract_point_cloud_arrays(weight_threshold)
+        return PointCloud(p, n)
+
+
+def depth_prepare(raw: torch.Tensor, nears, fars, conf: Optional[torch.Tensor] = None,
+                  count: Optional[torch.Tensor] = None, has_conf: Optional[torch.Tensor] = None,
+                  confidence_threshold: float = 0.0, valid_count_threshold: int = 0):
+    """K1 over [F,H,W] raw NDC depth: returns (linear float32 [F,H,W], frame_valid int32 [F])."""
+    if raw.dim() != 3 or raw.dtype != torch.float32 or not raw.is_cuda:
+        raise RuntimeError("raw must be a float32 CUDA tensor [F,H,W]")
+    raw = raw.contiguous()
+    F, H, W = raw.shape
+    near = _as_np(nears, np.float64, (F,))
+    far = _as_np(fars, np.float64, (F,))
+    out = torch.empty_like(raw)
+    valid = torch.empty((F,), dtype=torch.int32, device=raw.device)
+    if conf is not None:
+        conf = conf.to(raw.device).to(torch.float64).contiguous()
+        count = count.to(raw.device).to(torch.int32).contiguous()
+        if has_conf is not None:
+            has_conf = has_conf.to(raw.device).to(torch.uint8).contiguous()
+    with torch.cuda.device(raw.device):
+        _lib.check(_lib.lib().mq3d_depth_prepare(_lib.dptr(raw), F, W, H, _lib.darr(near), _lib.darr(far),
+                                                 _lib.dptr(conf), _lib.dptr(count), _lib.dptr(has_conf),
+                                                 C.c_double(confidence_threshold), int(valid_count_threshold),
+                                                 _lib.dptr(out), _lib.dptr(valid), _stream()))
+    return out, valid
+
+
+def estimate_confidence(depths: torch.Tensor, K, Ecw, Ecw_inv, target_frame_range: int, depth_max: float,
+                        error_threshold: float, frame_valid: Optional[torch.Tensor] = None):
+    """K4 over one side: returns (confidence float64 [F,H,W], valid_count int32 [F,H,W])."""
+    if depths.dim() != 3 or depths.dtype != torch.float32 or not depths.is_cuda:
+        raise RuntimeError("depths must be a float32 CUDA tensor [F,H,W]")
+    depths = depths.contiguous()
+    F, H, W = depths.shape
+    K = _as_np(K, np.float32, (F, 3, 3))
+    Ecw = _as_np(Ecw, np.float32, (F, 4, 4))
+    Einv = _as_np(Ecw_inv, np.float32, (F, 4, 4))
+    conf = torch.zeros((F, H, W), dtype=torch.float64, device=depths.device)
+    cnt = torch.zeros((F, H, W), dtype=torch.int32, device=depths.device)
+    fv = frame_valid.to(depths.device).to(torch.int32).contiguous() if frame_valid is not None else None
+    with torch.cuda.device(depths.device):
+        _lib.check(_lib.lib().mq3d_confidence(_lib.dptr(depths), _lib.dptr(fv), F, W, H, _lib.farr(K), _lib.farr(Ecw),
+                                              _lib.farr(Einv), int(target_frame_range), C.c_double(depth_max),
+                                              C.c_double(error_threshold), _lib.dptr(conf), _lib.dptr(cnt), _stream()))
+    return conf, cnt
