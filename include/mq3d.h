@@ -42,6 +42,10 @@ typedef struct mq3d_scene mq3d_scene; /* RaycastingScene state: triangles + LBVH
 
 const char *mq3d_last_error(void);
 int mq3d_version(void);
+/* Self-test used by the parity suite: number of floats with bit pattern in [lo_bits, hi_bits] (both
+ * signs) for which the kernels' branch-free reciprocal differs from the IEEE round-to-nearest
+ * reciprocal.  Must be 0 over the normal range [0x00800000, 0x7E800000]. */
+int mq3d_selftest_rcp(unsigned lo_bits, unsigned hi_bits, unsigned long long *n_bad_out);
 
 /* ---- voxel block grid life cycle ------------------------------------------------------------
  * Replaces o3d.t.geometry.VoxelBlockGrid(attr_names, attr_dtypes, attr_channels, voxel_size,
@@ -113,6 +117,8 @@ typedef struct {
     int64_t num_blocks;        /* active blocks after the call */
     int64_t batches;
     int64_t voxel_updates;     /* voxel visits that passed every reject (updated-voxel count) */
+    double touch_ms;           /* device time of the K2 launches (CUDA events on `stream`) */
+    double integrate_ms;       /* device time of the K3 launches (CUDA events on `stream`) */
 } mq3d_seq_stats;
 
 /* Fused replacement of the whole per-frame loop of integrate() (o3d_utils.py:231-236):

@@ -22,7 +22,7 @@ ATTR_COLOR = 2
 
 # every symbol include/mq3d.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "mq3d_last_error", "mq3d_version",
+    "mq3d_last_error", "mq3d_version", "mq3d_selftest_rcp",
     "mq3d_grid_create", "mq3d_grid_destroy", "mq3d_grid_reset", "mq3d_grid_reserve",
     "mq3d_grid_num_blocks", "mq3d_grid_info", "mq3d_grid_pool", "mq3d_grid_export", "mq3d_grid_import",
     "mq3d_grid_set_partition",
@@ -37,7 +37,7 @@ SYMBOLS = [
 class SeqStats(C.Structure):
     _fields_ = [("frames_integrated", C.c_int64), ("block_visits", C.c_int64),
                 ("blocks_loaded", C.c_int64), ("num_blocks", C.c_int64), ("batches", C.c_int64),
-                ("voxel_updates", C.c_int64)]
+                ("voxel_updates", C.c_int64), ("touch_ms", C.c_double), ("integrate_ms", C.c_double)]
 
 
 class Mq3dError(RuntimeError):
@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
     pd = C.POINTER(C.c_double)
     pf = C.POINTER(C.c_float)
     sig = {
+        "mq3d_selftest_rcp": [C.c_uint, C.c_uint, C.POINTER(C.c_ulonglong)],
         "mq3d_grid_create": [f32, i32, i64, i32, i32, C.POINTER(vp)],
         "mq3d_grid_destroy": [vp],
         "mq3d_grid_reset": [vp, vp],

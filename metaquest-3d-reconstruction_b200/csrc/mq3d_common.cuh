@@ -197,11 +197,24 @@ struct mq3d_grid {
     int bitmap_words;
     int *stamp;           // [table_size] batch serial of last touch
     int *slot_list;       // [table_size] slots touched in the current batch
+    int *slot_sorted;     // [table_size] same, heavy-first (LPT order for the dynamic scheduler)
+    // colour scratch of the fused path: packed RGBX frames and per-frame depth->colour pixel LUTs
+    uint32_t *rgbx;
+    int64_t rgbx_px;
+    int *color_lut;
+    int64_t color_lut_size;
+    // validated fast division by the truncation constant
+    float div_checked_trunc;
+    int div_fast_ok;
     int batch_serial;
     FrameParams *frame_params_dev;  // [MQ3D_MAX_BATCH]
     int32_t *idx_scratch;  // per-frame integrate: block index per key
     int64_t idx_scratch_size;
     int *pinned_host;     // pinned int[8] for async readbacks
+    int *frame_counts_dev;             // [MQ3D_MAX_BATCH]
+    unsigned long long *stat_dev;      // [2]
+    cudaEvent_t *events;               // persistent timing events of the sequence path
+    int n_events;
     // marching cubes scratch (valid between *_count and *_fill)
     int32_t *mc_nb;       // [n][27]
     uint32_t *mc_emask;   // [n][384]

@@ -97,7 +97,7 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
         hp[i].pad = 0;
     }
     NdcParams *dp = nullptr;
-    cudaError_t e = cudaMalloc(&dp, sizeof(NdcParams) * n_frames);
+    cudaError_t e = cudaMallocAsync(&dp, sizeof(NdcParams) * n_frames, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dp, hp, sizeof(NdcParams) * n_frames, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(frame_valid_dev, 0, sizeof(int32_t) * n_frames, st);
     if (e == cudaSuccess) {
@@ -106,7 +106,7 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
                        (conf_dev == nullptr || ((((uintptr_t)conf_dev | (uintptr_t)count_dev) & 15) == 0));
         if (!aligned) {
             free(hp);
-            cudaFree(dp);
+            cudaFreeAsync(dp, st);
             mq3d_set_error("depth_prepare: buffers must be 16-byte aligned and W*H a multiple of 4");
             return MQ3D_ERR_INVALID;
         }
@@ -124,7 +124,7 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // hp/dp lifetime
     free(hp);
-    cudaFree(dp);
+    cudaFreeAsync(dp, st);
     if (e != cudaSuccess) {
         mq3d_set_error("depth_prepare: %s", cudaGetErrorString(e));
         return MQ3D_ERR_CUDA;

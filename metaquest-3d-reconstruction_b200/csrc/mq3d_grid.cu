@@ -76,6 +76,9 @@ static int alloc_slot_scratch(mq3d_grid *g, cudaStream_t st) {
     if (g->bitmap) cudaFree(g->bitmap);
     if (g->stamp) cudaFree(g->stamp);
     if (g->slot_list) cudaFree(g->slot_list);
+    if (g->slot_sorted) cudaFree(g->slot_sorted);
+    g->slot_sorted = nullptr;
+    MQ3D_CUDA(cudaMalloc(&g->slot_sorted, sizeof(int) * g->table_size));
     g->bitmap_words = MQ3D_MAX_BATCH / 32;
     MQ3D_CUDA(cudaMalloc(&g->bitmap, sizeof(uint32_t) * g->table_size * g->bitmap_words));
     MQ3D_CUDA(cudaMalloc(&g->stamp, sizeof(int) * g->table_size));
@@ -131,6 +134,8 @@ extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t 
             MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * 8, st));
             MQ3D_CUDA(cudaMalloc(&g->frame_params_dev, sizeof(FrameParams) * MQ3D_MAX_BATCH));
             MQ3D_CUDA(cudaMallocHost(&g->pinned_host, sizeof(int) * 8));
+            MQ3D_CUDA(cudaMalloc(&g->frame_counts_dev, sizeof(int) * MQ3D_MAX_BATCH));
+            MQ3D_CUDA(cudaMalloc(&g->stat_dev, sizeof(unsigned long long) * 2));
             return MQ3D_OK;
         }();
     }
@@ -183,9 +188,16 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->bitmap);
     cudaFree(g->stamp);
     cudaFree(g->slot_list);
+    cudaFree(g->slot_sorted);
+    cudaFree(g->rgbx);
+    cudaFree(g->color_lut);
     cudaFree(g->frame_params_dev);
     cudaFree(g->idx_scratch);
     if (g->pinned_host) cudaFreeHost(g->pinned_host);
+    cudaFree(g->frame_counts_dev);
+    cudaFree(g->stat_dev);
+    for (int q = 0; q < g->n_events; ++q) cudaEventDestroy(g->events[q]);
+    free(g->events);
     free_mc(g);
     delete g;
     return MQ3D_OK;

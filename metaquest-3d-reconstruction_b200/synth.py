@@ -2,7 +2,7 @@
 
 Analytic scene (Unity world, Y up): room 5.0 x 3.0 x 4.0 m centred at (0,1.5,0), a sphere
 r=0.5 m at (0.8,1.0,-0.5) and a 1.0 x 0.8 x 0.6 m box standing on the floor.  The head moves on a
-circle (r=0.8 m, height 1.5 m) sweeping yaw with a +-15 deg sinusoidal pitch; eyes sit +-31.5 mm
+circle (r=0.5 m, height 1.5 m) sweeping yaw with a +-15 deg sinusoidal pitch; eyes sit +-31.5 mm
 along head-right.  Depth frames are 320x320 raw NDC (`d = 1 - near/z`, far = inf) sampled at
 integer pixel coordinates, with multiplicative Gaussian noise and 2 % dropped pixels (raw 1.0 ->
 linear 0).  Poses are emitted in Unity convention so they traverse the same
@@ -33,6 +33,7 @@ DEPTH_W = DEPTH_H = 320
 NEAR = 0.1
 FAR = float("inf")
 IPD_HALF = 0.0315
+HEAD_RADIUS = 0.5
 COLOR_W, COLOR_H = 1280, 960
 COLOR_F = 870.0
 
@@ -50,7 +51,9 @@ def head_trajectory(n_frames: int, sweep_frames: int = 900):
     yaw = 2.0 * np.pi * i / sweep_frames
     pitch = np.deg2rad(15.0) * np.sin(2.0 * np.pi * i / 120.0)
     # head centre travels on a circle, looking outward-ish (yaw follows the angle)
-    pos = np.stack([0.8 * np.sin(yaw), np.full_like(yaw, 1.5), 0.8 * np.cos(yaw)], axis=1)
+    # r = 0.5 m (SURVEY 8d proposed 0.8 m, but that path grazes the sphere: depths below the near
+    # plane make raw NDC negative and is_depth_map_valid rejects ~50 of every 300 frames)
+    pos = np.stack([HEAD_RADIUS * np.sin(yaw), np.full_like(yaw, 1.5), HEAD_RADIUS * np.cos(yaw)], axis=1)
     # Unity: +Y up, left-handed; yaw about +Y then pitch about local +X
     rot = Rotation.from_euler("y", yaw[:, None]) * Rotation.from_euler("x", pitch[:, None])
     return pos, rot

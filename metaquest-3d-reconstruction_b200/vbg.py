@@ -72,6 +72,8 @@ class SequenceStats:
     num_blocks: int
     batches: int
     voxel_updates: int
+    touch_ms: float = 0.0
+    integrate_ms: float = 0.0
 
     @property
     def voxel_visits(self) -> int:
@@ -236,7 +238,7 @@ class VoxelBlockGrid:
                 _lib.darr(Kc), _lib.darr(E), C.c_float(depth_scale), C.c_float(depth_max),
                 C.c_float(trunc_voxel_multiplier), int(batch_frames), C.byref(st), _stream()))
         return SequenceStats(st.frames_integrated, st.block_visits, st.blocks_loaded, st.num_blocks, st.batches,
-                             st.voxel_updates)
+                             st.voxel_updates, st.touch_ms, st.integrate_ms)
 
     # -- pool views / persistence -------------------------------------------------------------------
     def _pool_ptrs(self):
