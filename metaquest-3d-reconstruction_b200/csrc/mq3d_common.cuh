@@ -203,6 +203,8 @@ struct mq3d_grid {
     int64_t rgbx_px;
     int *color_lut;
     int64_t color_lut_size;
+    float *depth_scratch;   // frames / depth_scale when depth_scale != 1
+    int64_t depth_scratch_size;
     // validated fast division by the truncation constant
     float div_checked_trunc;
     int div_fast_ok;

@@ -96,8 +96,20 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
         }
         hp[i].pad = 0;
     }
-    NdcParams *dp = nullptr;
-    cudaError_t e = cudaMallocAsync(&dp, sizeof(NdcParams) * n_frames, st);
+    // per-device parameter scratch, kept across calls (one stream per device by contract)
+    static NdcParams *s_dp[64] = {nullptr};
+    static int s_dp_cap[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev < 64 && n_frames > s_dp_cap[dev]) {
+        cudaFree(s_dp[dev]);
+        s_dp[dev] = nullptr;
+        s_dp_cap[dev] = 0;
+        e = cudaMalloc(&s_dp[dev], sizeof(NdcParams) * n_frames);
+        if (e == cudaSuccess) s_dp_cap[dev] = n_frames;
+    }
+    NdcParams *dp = (e == cudaSuccess && dev < 64) ? s_dp[dev] : nullptr;
+    if (e == cudaSuccess && dp == nullptr) e = cudaErrorInvalidDevice;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dp, hp, sizeof(NdcParams) * n_frames, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(frame_valid_dev, 0, sizeof(int32_t) * n_frames, st);
     if (e == cudaSuccess) {
@@ -106,7 +118,6 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
                        (conf_dev == nullptr || ((((uintptr_t)conf_dev | (uintptr_t)count_dev) & 15) == 0));
         if (!aligned) {
             free(hp);
-            cudaFreeAsync(dp, st);
             mq3d_set_error("depth_prepare: buffers must be 16-byte aligned and W*H a multiple of 4");
             return MQ3D_ERR_INVALID;
         }
@@ -122,9 +133,7 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
         k_depth_finalize<<<(n_frames + 255) / 256, 256, 0, st>>>(frame_valid_dev, n_frames);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // hp/dp lifetime
-    free(hp);
-    cudaFreeAsync(dp, st);
+    free(hp);  // pageable H2D copies are staged before cudaMemcpyAsync returns
     if (e != cudaSuccess) {
         mq3d_set_error("depth_prepare: %s", cudaGetErrorString(e));
         return MQ3D_ERR_CUDA;

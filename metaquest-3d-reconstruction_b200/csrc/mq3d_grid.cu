@@ -189,6 +189,7 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->stamp);
     cudaFree(g->slot_list);
     cudaFree(g->slot_sorted);
+    cudaFree(g->depth_scratch);
     cudaFree(g->rgbx);
     cudaFree(g->color_lut);
     cudaFree(g->frame_params_dev);

@@ -189,7 +189,7 @@ __global__ void k_refit(int n, const int *__restrict__ left, const int *__restri
         }
         for (int a = 0; a < 3; ++a) {
             node_box[6 * (int64_t)cur + a] = fminf(l[a], r[a]);
-            node_box[6 * (int64_t)cur + 3 + a] = fmaxf(l[a], r[a]);
+            node_box[6 * (int64_t)cur + 3 + a] = fmaxf(l[3 + a], r[3 + a]);
         }
         BvhNode nd;
         nd.a = make_float4(l[0], l[1], l[2], l[3]);
@@ -414,4 +414,12 @@ extern "C" int mq3d_scene_cast_rays(mq3d_scene *s, const float *rays_dev, int64_
                                                                                   n_rays, t_hit_dev);
     MQ3D_CUDA(cudaGetLastError());
     return MQ3D_OK;
+}
+
+// debug helper (not part of the public ABI): copy the first `max_nodes` BVH nodes to the host
+extern "C" int mq3d_scene_debug_nodes(mq3d_scene *s, void *out_host, int max_nodes) {
+    int n = (int)(s->n_tris > 1 ? s->n_tris - 1 : 0);
+    if (n > max_nodes) n = max_nodes;
+    MQ3D_CUDA(cudaMemcpy(out_host, s->nodes, sizeof(BvhNode) * n, cudaMemcpyDeviceToHost));
+    return n;
 }

@@ -1,0 +1,76 @@
+"""GPU parity: colour integration (Open3D colour overload of Integrate) vs the oracle.
+There is no reference call site for this overload, so it is pinned to the oracle restatement only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import capture, oracle_integrate_sequence, pipeline_cameras, sort_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(oracle, n=6, cw=160, ch=120):
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    cap = capture(n)
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = np.stack([oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i]) for i in range(n)])
+    f = 110.0
+    colors = np.stack([synth.make_color_frame(Ecw[i], width=cw, height=ch, f=f) for i in range(n)])
+    Kc = np.tile(np.array([[f, 0, cw / 2.0], [0, f, ch / 2.0], [0, 0, 1.0]]), (n, 1, 1))
+    return lin, K, Ewc, colors, Kc
+
+
+@pytest.mark.parametrize("batch", [1, 64])
+def test_color_sequence_matches_oracle(cuda_device, oracle, batch):
+    from mq3d_b200.vbg import VoxelBlockGrid
+    lin, K, Ewc, colors, Kc = _setup(oracle)
+    og = oracle.Grid(0.02, with_color=True)
+    oracle_integrate_sequence(oracle, og, lin, K, Ewc, 4.0, 10.0, colors=colors, Kc=Kc)
+    vbg = VoxelBlockGrid(attr_names=("tsdf", "weight", "color"), voxel_size=0.02, block_count=500, device=cuda_device)
+    vbg.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, 4.0, 10.0,
+                           colors=torch.from_numpy(colors).to(cuda_device), color_intrinsics=Kc, batch_frames=batch)
+    k0, t0, w0, c0 = sort_blocks(*og.export())
+    k1, t1, w1, c1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
+    assert c0.max() > 100 and (c0.sum(-1) > 0).mean() > 0.2      # colour was actually written
+
+
+def test_color_per_frame_matches_oracle(cuda_device, oracle):
+    from mq3d_b200.vbg import VoxelBlockGrid
+    lin, K, Ewc, colors, Kc = _setup(oracle, n=3)
+    og = oracle.Grid(0.02, with_color=True)
+    vbg = VoxelBlockGrid(attr_names=("tsdf", "weight", "color"), voxel_size=0.02, block_count=500, device=cuda_device)
+    for i in range(3):
+        keys = og.touch(lin[i], K[i], Ewc[i], 4.0, 10.0)
+        og.integrate(keys, lin[i], K[i], Ewc[i], 4.0, 10.0, color=colors[i], Kc=Kc[i])
+        vbg.integrate(keys, lin[i], colors[i], K[i].astype(np.float64), Kc[i], Ewc[i].astype(np.float64), 1.0, 4.0, 10.0)
+    k0, t0, w0, c0 = sort_blocks(*og.export())
+    k1, t1, w1, c1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
+
+
+def test_depth_scale_is_applied(cuda_device, oracle):
+    """depth_scale != 1 (never used by the reference, supported by Open3D): depth / scale per sample."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    cap = capture(2)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = np.stack([oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i]) for i in range(2)])
+    mm = (lin * np.float32(1000.0)).astype(np.float32)
+    og = oracle.Grid(0.02)
+    vbg = VoxelBlockGrid(voxel_size=0.02, block_count=500, device=cuda_device)
+    for i in range(2):
+        okeys = og.touch(mm[i], K[i], Ewc[i], 4.0, 10.0, depth_scale=1000.0)
+        keys = vbg.compute_unique_block_coordinates(mm[i], K[i].astype(np.float64), Ewc[i].astype(np.float64), 1000.0, 4.0, 10.0)
+        assert {tuple(k) for k in keys.cpu().numpy().tolist()} == {tuple(k) for k in okeys.tolist()}
+        og.integrate(okeys, mm[i], K[i], Ewc[i], 4.0, 10.0, depth_scale=1000.0)
+        vbg.integrate(keys, mm[i], K[i].astype(np.float64), Ewc[i].astype(np.float64), 1000.0, 4.0, 10.0)
+    k0, t0, w0 = sort_blocks(*og.export()[:3])
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
