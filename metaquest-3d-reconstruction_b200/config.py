@@ -1,0 +1,211 @@
+"""``pipeline_config.yml: reconstruction:`` parser -- same keys, defaults and coercions as the
+reference's config/reconstruction_config.py:32-253, without importing open3d.
+
+Differences that follow from the north star ("no CPU fallback"): ``device`` is a plain string and
+must name a CUDA device; the reference's silent CUDA->CPU fallback (reconstruction_config.py:21-29)
+becomes a RuntimeError.  A config written for the reference with ``device: "CPU:0"`` is accepted
+only when ``allow_device_override=True`` remaps it to ``CUDA:0``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, fields, is_dataclass
+from pathlib import Path
+from typing import Any, get_args, get_origin, get_type_hints
+
+import yaml
+
+
+def get_available_device(device_str: str, allow_device_override: bool = True) -> str:
+    """Validate the device string.  'CUDA:N' is returned as is; 'CPU:0' (the reference default,
+    pipeline_config.yml:14) is remapped to 'CUDA:0' when overriding is allowed, else rejected."""
+    s = str(device_str).strip().upper()
+    if s.startswith("CUDA"):
+        return s if ":" in s else s + ":0"
+    if allow_device_override:
+        print(f"[Warning] Device '{device_str}' requested; this build only runs on CUDA devices -> using CUDA:0")
+        return "CUDA:0"
+    raise RuntimeError(f"Device '{device_str}' is not a CUDA device and this build has no CPU fallback")
+
+
+@dataclass
+class DepthConfidenceEstimationConfig:
+    target_frame_range: int = 10
+    depth_max: float = 3.0
+    error_threshold: float = 0.05
+    skip_if_output_dir_exists: bool = True
+    use_dataset_cache: bool = True
+    use_multi_threading: bool = True      # accepted for compatibility; one GPU launch per side replaces the Pool
+
+
+@dataclass
+class FragmentGenerationConfig:
+    device: str
+    fragment_size: int = 100
+    use_confidence_filtered_depth: bool = True
+    confidence_threshold: float = 0.05
+    valid_count_threshold: int = 4
+    depth_max: float = 3.0
+    odometry_loop_interval: int = 10
+    overlap_ratio_threshold: float = 0.1
+    loop_yaw_info_density_threshold: float = 0.3
+    dist_threshold: float = 0.07
+    edge_prune_threshold: float = 0.25
+    use_dataset_cache: bool = True
+    use_multi_threading: bool = False
+
+
+@dataclass
+class FragmentPoseRefinementConfig:
+    device: str
+    use_confidence_filtered_depth: bool = True
+    confidence_threshold: float = 0.05
+    valid_count_threshold: int = 4
+    voxel_size: float = 0.01
+    block_resolution: int = 16
+    block_count: int = 50_000
+    depth_max: float = 1.5
+    trunc_voxel_multiplier: float = 8.0
+    use_pre_filtering: bool = True
+    pre_filter_every_k_points: float = 30
+    pre_filter_max_corr_dist: float = 0.1
+    pre_filter_inlier_rmse_threshold: float = 0.05
+    pre_filter_fitness_threshold: float = 0.2
+    icp_voxel_sizes: list[float] = field(default_factory=lambda: [0.05, 0.025, 0.0125])
+    max_corr_dists: list[float] = field(default_factory=lambda: [0.1, 0.05, 0.025])
+    max_iterations: list[int] = field(default_factory=lambda: [50, 31, 14])
+    relative_fitnesses: list[float] = field(default_factory=lambda: [1e-6, 1e-6, 1e-6])
+    relative_rmses: list[float] = field(default_factory=lambda: [1e-6, 1e-6, 1e-6])
+    icp_fitness_threshold: float = 0.2
+    icp_inlier_rmse_threshold: float = 0.05
+    dist_threshold: float = 0.07
+    edge_prune_threshold: float = 0.25
+    use_multi_threading: bool = False
+
+
+@dataclass
+class IntegrationConfig:
+    device: str
+    use_confidence_filtered_depth: bool = True
+    confidence_threshold: float = 0.05
+    valid_count_threshold: int = 4
+    voxel_size: float = 0.01
+    block_resolution: int = 16
+    block_count: int = 50_000
+    depth_max: float = 1.5
+    trunc_voxel_multiplier: float = 8.0
+
+
+@dataclass
+class ColorOptimizationConfig:
+    device: str
+    weight_threshold: float = 3.0
+    estimated_vertex_number: int = -1
+    interval: int = 10
+    max_iteration: int = 100
+    use_dataset_cache: bool = True
+    min_triangle_count: int = 2000
+
+
+@dataclass
+class ColorAlignedDepthRenderingConfig:
+    weight_threshold: float = 3.0
+    estimated_vertex_number: int = -1
+    min_triangle_count: int = 2000
+    only_use_optimized_dataset: bool = True
+
+
+@dataclass
+class ReconstructionConfig:
+    device: str = "CUDA:0"
+    use_dataset_cache: bool = True
+    estimate_depth_confidences: bool = True
+    optimize_depth_pose: bool = True
+    use_fragment_dataset_cache: bool = True
+    use_optimized_dataset_cache: bool = True
+    use_colorless_vbg_cache: bool = True
+    visualize_colorless_pcd: bool = True
+    optimize_color_pose: bool = True
+    visualize_colored_mesh: bool = True
+    sample_point_cloud_from_colored_mesh: bool = True
+    points_per_vertex_ratio: float = 1.0
+    render_color_aligned_depth: bool = True
+
+    confidence_estimation: DepthConfidenceEstimationConfig = field(init=False)
+    fragment_generation: FragmentGenerationConfig = field(init=False)
+    fragment_pose_refinement: FragmentPoseRefinementConfig = field(init=False)
+    depth_integration: IntegrationConfig = field(init=False)
+    color_optimization: ColorOptimizationConfig = field(init=False)
+    color_aligned_depth_rendering: ColorAlignedDepthRenderingConfig = field(init=False)
+
+    def __post_init__(self):
+        self.confidence_estimation = DepthConfidenceEstimationConfig()
+        self.fragment_generation = FragmentGenerationConfig(device=self.device)
+        self.fragment_pose_refinement = FragmentPoseRefinementConfig(device=self.device)
+        self.depth_integration = IntegrationConfig(device=self.device)
+        self.color_optimization = ColorOptimizationConfig(device=self.device)
+        self.color_aligned_depth_rendering = ColorAlignedDepthRenderingConfig()
+        if self.use_dataset_cache:
+            for sub in vars(self).values():
+                if hasattr(sub, "use_dataset_cache"):
+                    sub.use_dataset_cache = True
+
+    @classmethod
+    def parse(cls, config_dict: dict[str, Any], allow_device_override: bool = True) -> "ReconstructionConfig":
+        """reconstruction_config.py:184-253: typed coercion, sub-configs inherit `device`."""
+        device = get_available_device(str(config_dict.get("device", "CUDA:0")), allow_device_override)
+
+        def coerce(hint, value):
+            if hint is float and isinstance(value, (str, int)) and not isinstance(value, bool):
+                return float(value)
+            if hint is int and isinstance(value, str):
+                return int(value)
+            if hint is bool and isinstance(value, str):
+                return value.lower() in ("true", "1")
+            if get_origin(hint) is list and isinstance(value, list):
+                sub = get_args(hint)[0]
+                return [coerce(sub, v) for v in value]
+            return value
+
+        def build(dc, d):
+            hints = get_type_hints(dc)
+            kwargs, late = {}, {}
+            for f in fields(dc):
+                if f.name not in d:
+                    continue
+                hint, value = hints[f.name], d[f.name]
+                if f.name == "device":
+                    value = get_available_device(str(value), allow_device_override)
+                elif is_dataclass(hint) and isinstance(value, dict):
+                    value = build(hint, value)
+                else:
+                    value = coerce(hint, value)
+                (kwargs if f.init else late)[f.name] = value
+            if any(f.name == "device" for f in fields(dc)) and "device" not in kwargs:
+                kwargs["device"] = device
+            obj = dc(**kwargs)
+            for k, v in late.items():
+                setattr(obj, k, v)
+            return obj
+
+        cfg = build(cls, dict(config_dict, device=device))
+        if cfg.use_dataset_cache:
+            for sub in vars(cfg).values():
+                if hasattr(sub, "use_dataset_cache") and sub.use_dataset_cache is not False:
+                    sub.use_dataset_cache = True
+        return cfg
+
+
+@dataclass
+class PipelineConfigs:
+    """Only the ``reconstruction:`` section is on the hot path; the other sections are kept as raw dicts
+    (config/pipeline_configs.py:10-30)."""
+    reconstruction: ReconstructionConfig
+    yuv_to_rgb: dict = field(default_factory=dict)
+    depth_to_linear: dict = field(default_factory=dict)
+
+    @classmethod
+    def parse_config_yml(cls, yml_path: Path, allow_device_override: bool = True) -> "PipelineConfigs":
+        with open(yml_path, "r") as f:
+            d = yaml.safe_load(f)
+        return cls(reconstruction=ReconstructionConfig.parse(d["reconstruction"], allow_device_override),
+                   yuv_to_rgb=d.get("yuv_to_rgb", {}), depth_to_linear=d.get("depth_to_linear", {}))

@@ -1,0 +1,120 @@
+"""``reconstruct_scene(data_io, config)`` -- the stage driver of the reference
+(processing/reconstruction/reconstruct_scene.py:19-225) with the volumetric hot path on the GPU.
+
+Kept: stage order, caches, artefacts on disk (colorless_vbg.npz, colorless.ply, colorless_mesh_*.ply,
+<side>_color_aligned_depth/<ts>.npy), LEFT fully integrated before RIGHT into one grid.
+Out of scope: depth-pose optimisation (ICP / pose graph) and the legacy
+colour-map optimiser -- requesting them raises, they are not silently skipped.  Interactive viewers
+are ignored.
+"""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+from .config import ReconstructionConfig
+from .dataio import DataIO
+from .models import CoordinateSystem, DepthDataset, Side
+from .ops import estimate_depth_confidences, filter_mesh_components, integrate, raycast_in_color_view
+from .raycast import RaycastingScene
+from .vbg import VoxelBlockGrid
+
+
+def log_step(title: str):
+    print("\n" + "=" * 60 + f"\n[Step] {title}\n" + "=" * 60)
+
+
+def reconstruct_scene(data_io: DataIO, config: ReconstructionConfig, strict: bool = False) -> dict:
+    """Returns a dict of timings/sizes (the reference returns None; callers that ignore it are unaffected)."""
+    report: dict = {}
+    if config.optimize_depth_pose or config.optimize_color_pose:
+        msg = ("optimize_depth_pose / optimize_color_pose (multi-scale ICP, pose-graph and colour-map "
+               "optimisation) are outside this hot-path build; set them to false")
+        if strict:
+            raise RuntimeError(msg)
+        print(f"[Warning] {msg} -- continuing without them")
+
+    # Dataset generation (reconstruct_scene.py:21-24)
+    if not config.use_dataset_cache:
+        for side in Side:
+            data_io.depth.depth_datasets.pop(side, None)
+            data_io.depth.load_depth_dataset(side=side, use_cache=False)
+
+    # Depth confidence estimation (:27-32)
+    confidences = {}
+    if config.estimate_depth_confidences:
+        log_step("Estimate depth confidences")
+        t0 = time.perf_counter()
+        confidences = estimate_depth_confidences(depth_data_io=data_io.depth, config=config.confidence_estimation,
+                                                 device=config.device)
+        report["confidence_s"] = time.perf_counter() - t0
+
+    # Depth datasets in Open3D convention (:43-53)
+    depth_dataset_map: dict[Side, DepthDataset] = {}
+    for side in Side:
+        ds = data_io.depth.load_depth_dataset(side=side, use_cache=config.fragment_generation.use_dataset_cache)
+        ds.transforms = ds.transforms.convert_coordinate_system(CoordinateSystem.OPEN3D, is_camera=True)
+        depth_dataset_map[side] = ds
+
+    # TSDF integration (:55-81)
+    vbg: Optional[VoxelBlockGrid] = None
+    if config.use_colorless_vbg_cache:
+        vbg = data_io.reconstruction.load_colorless_vbg(device=config.device)
+    if vbg is None:
+        log_step("Integrate depth maps")
+        ic = config.depth_integration
+        t0 = time.perf_counter()
+        for side, dataset in depth_dataset_map.items():
+            vbg = integrate(dataset=dataset, depth_data_io=data_io.depth, side=side,
+                            use_confidence_filtered_depth=ic.use_confidence_filtered_depth,
+                            confidence_threshold=ic.confidence_threshold,
+                            valid_count_threshold=ic.valid_count_threshold, voxel_size=ic.voxel_size,
+                            block_resolution=ic.block_resolution, block_count=ic.block_count,
+                            depth_max=ic.depth_max, trunc_voxel_multiplier=ic.trunc_voxel_multiplier,
+                            device=ic.device, show_progress=True, desc=f"[{side.name}] Integrating depth maps ...",
+                            vbg_opt=vbg, confidence=confidences.get(side))
+        report["integrate_s"] = time.perf_counter() - t0
+    if vbg is None:
+        print("[Error] Failed to generate VoxelBlockGrid. Please check the integration parameters and input data.")
+        return report
+    report["active_blocks"] = vbg.num_blocks()
+    data_io.reconstruction.save_colorless_vbg(vbg=vbg)
+
+    # colourless point cloud (:89-91)
+    pcd = vbg.extract_point_cloud().to_legacy()
+    data_io.reconstruction.save_colorless_pcd_legacy(pcd=pcd)
+    report["points"] = len(pcd.points)
+
+    # colour-aligned depth rendering (:181-225)
+    if config.render_color_aligned_depth:
+        log_step("Render color-aligned depth")
+        t0 = time.perf_counter()
+        mesh = vbg.extract_triangle_mesh(weight_threshold=config.color_optimization.weight_threshold,
+                                         estimated_vertex_number=config.color_optimization.estimated_vertex_number)
+        data_io.reconstruction.save_colorless_mesh_raw_legacy(mesh=mesh.to_legacy())
+        report["mesh_raw"] = (int(mesh.vertex.positions.shape[0]), int(mesh.triangle.indices.shape[0]))
+        mesh = filter_mesh_components(mesh, min_triangle_count=config.color_optimization.min_triangle_count)
+        data_io.reconstruction.save_colorless_mesh_clean_legacy(mesh=mesh.to_legacy())
+        report["mesh_clean"] = (int(mesh.vertex.positions.shape[0]), int(mesh.triangle.indices.shape[0]))
+        report["mesh_s"] = time.perf_counter() - t0
+        scene = RaycastingScene(device=config.device)
+        scene.add_triangles(mesh)
+        rendered = 0
+        t0 = time.perf_counter()
+        for side in Side:
+            try:
+                color_dataset = data_io.color.load_color_dataset(side=side, use_cache=True)
+            except FileNotFoundError as e:
+                print(f"[Warning] {e}")
+                continue
+            # optimised colour datasets do not exist in this build (no colour-map optimiser), so the
+            # reference's `only_use_optimized_dataset` gate (:211-225) decides whether anything is rendered
+            if config.color_aligned_depth_rendering.only_use_optimized_dataset:
+                continue
+            for i, depth_map in enumerate(raycast_in_color_view(scene=scene, dataset=color_dataset)):
+                data_io.rgbd.save_color_aligned_depth(depth_map=depth_map, side=side,
+                                                      timestamp=color_dataset.timestamps[i])
+                rendered += 1
+        report["raycast_frames"] = rendered
+        report["raycast_s"] = time.perf_counter() - t0
+    return report

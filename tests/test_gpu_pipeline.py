@@ -1,0 +1,133 @@
+"""GPU: the reference-facing surface end to end -- DataIO project on disk -> reconstruct_scene()
+(confidence -> integrate LEFT then RIGHT -> save -> extract -> raycast), checked against the same
+pipeline assembled from the CPU oracle; and the Open3D-shaped compat layer driving the per-frame loop
+exactly as the reference's o3d_utils.integrate does."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import pipeline_cameras, sort_blocks
+
+pytestmark = pytest.mark.gpu
+
+N = 10
+W = H = 96
+
+
+def _config():
+    from mq3d_b200.config import ReconstructionConfig
+    return ReconstructionConfig.parse({
+        "device": "CUDA:0", "use_dataset_cache": False, "estimate_depth_confidences": True,
+        "optimize_depth_pose": False, "optimize_color_pose": False, "use_colorless_vbg_cache": False,
+        "render_color_aligned_depth": True,
+        "confidence_estimation": {"target_frame_range": 3, "depth_max": 4.0, "error_threshold": 0.08,
+                                  "skip_if_output_dir_exists": False},
+        "depth_integration": {"use_confidence_filtered_depth": True, "confidence_threshold": 0.02,
+                              "valid_count_threshold": 2, "voxel_size": 0.03, "block_count": 64, "depth_max": 4.0,
+                              "trunc_voxel_multiplier": 10.0},
+        "color_optimization": {"weight_threshold": 1.5, "min_triangle_count": 50},
+        "color_aligned_depth_rendering": {"only_use_optimized_dataset": False},
+    })
+
+
+def test_reconstruct_scene_matches_oracle_pipeline(cuda_device, oracle, tmp_path):
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    from mq3d_b200.dataio import DataIO
+    from mq3d_b200.io_utils import read_ply
+    from mq3d_b200.models import CoordinateSystem, Side
+    from mq3d_b200.reconstruct import reconstruct_scene
+    from mq3d_b200.vbg import VoxelBlockGrid
+
+    caps = synth.write_project(tmp_path, N, width=W, height=H)
+    # one corrupt frame: all ones -> is_depth_map_valid rejects it -> dropped from the dataset
+    bad_ts = int(caps[Side.LEFT].dataset.timestamps[4])
+    np.ones((H, W), "<f4").tofile(tmp_path / "left_depth" / f"{bad_ts}.raw")
+    data_io = DataIO(tmp_path)
+    cds = synth.make_color_dataset(3, Side.LEFT)
+    cds.widths[:], cds.heights[:] = 128, 96
+    cds.fx[:], cds.fy[:], cds.cx[:], cds.cy[:] = 87, 87, 64, 48
+    cds.transforms = cds.transforms.convert_coordinate_system(CoordinateSystem.OPEN3D, is_camera=True)
+    data_io.color.save_color_dataset(Side.LEFT, cds)
+
+    cfg = _config()
+    report = reconstruct_scene(data_io, cfg)
+    assert report["active_blocks"] > 50 and report["raycast_frames"] == 3
+
+    # ---- the same pipeline from oracle parts ------------------------------------------------------
+    og = oracle.Grid(0.03)
+    for side in Side:
+        ds = data_io.depth.load_depth_dataset(side)
+        keep = [i for i in range(N) if not (side == Side.LEFT and i == 4)]
+        assert len(ds) == len(keep)
+        assert np.array_equal(ds.timestamps, caps[side].dataset.timestamps[keep])
+        raw = caps[side].raw[keep]
+        lin = np.stack([oracle.depth_to_linear(raw[i], ds.nears[i], ds.fars[i]) for i in range(len(ds))])
+        K, Ewc, Ecw = pipeline_cameras(ds) if ds.transforms.coordinate_system == CoordinateSystem.UNITY else (None,) * 3
+        if K is None:      # reconstruct_scene converted the cached dataset object in place
+            K = ds.get_intrinsic_matrices()
+            K[:, 0, 2] = ds.widths - K[:, 0, 2]
+            Ewc, Ecw = ds.transforms.extrinsics_wc, ds.transforms.extrinsics_cw
+        conf, count = oracle.confidence(lin, K, Ecw, np.linalg.inv(Ecw), 3, 4.0, 0.08)
+        for i in range(len(ds)):
+            cm = data_io.depth.load_confidence_map(side, ds.timestamps[i])       # files written by the GPU stage
+            assert np.array_equal(cm.valid_count, count[i]) and np.array_equal(cm.confidence_map, conf[i])
+            d = oracle.depth_mask(lin[i], conf[i], count[i], 0.02, 2)
+            keys = og.touch(d, K[i], Ewc[i], 4.0, 10.0)
+            og.integrate(keys, d, K[i], Ewc[i], 4.0, 10.0)
+    saved = VoxelBlockGrid.load(str(tmp_path / "reconstruction" / "colorless_vbg.npz"), device=cuda_device)
+    k0, t0, w0 = sort_blocks(*og.export()[:3])
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in saved.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    # artefacts
+    pts, _ = read_ply(tmp_path / "reconstruction" / "colorless.ply")
+    assert len(pts) == len(og.extract_points(3.0)[0]) == report["points"]
+    mv, mt = read_ply(tmp_path / "reconstruction" / "colorless_mesh_raw.ply")
+    ov, _, ot, _ = og.extract_mesh(1.5)
+    assert len(mv) == len(ov) and len(mt) == len(ot)
+    cv, ct = read_ply(tmp_path / "reconstruction" / "colorless_mesh_clean.ply")
+    assert 0 < len(ct) <= len(mt)
+    d0 = np.load(tmp_path / "left_color_aligned_depth" / f"{int(cds.timestamps[0])}.npy")
+    assert d0.shape == (96, 128) and d0.dtype == np.float32 and np.isfinite(d0).mean() > 0.3
+    assert 0.2 < np.median(d0[np.isfinite(d0)]) < 4.0
+
+
+def test_compat_layer_runs_the_reference_frame_loop(cuda_device, oracle):
+    """Body of o3d_utils.integrate (:171-236) written against `o3d` = mq3d_b200.compat."""
+    import mq3d_b200.compat as o3d
+    from helpers import capture
+    cap = capture(6)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    device = o3d.core.Device("CUDA:0")
+    vbg = o3d.t.geometry.VoxelBlockGrid(
+        attr_names=("tsdf", "weight"), attr_dtypes=(o3d.core.float32, o3d.core.float32), attr_channels=((1), (1)),
+        voxel_size=0.02, block_resolution=16, block_count=50, device=device)
+    og = oracle.Grid(0.02)
+    for index in range(len(ds)):
+        depth_np = oracle.depth_to_linear(cap.raw[index], ds.nears[index], ds.fars[index])
+        depth_map = o3d.t.geometry.Image(tensor=o3d.core.Tensor(depth_np, dtype=o3d.core.Dtype.Float32, device=device))
+        intrinsic = o3d.core.Tensor(K[index], dtype=o3d.core.Dtype.Float64)
+        extrinsic = o3d.core.Tensor(Ewc[index], dtype=o3d.core.Dtype.Float64)
+        coords = vbg.compute_unique_block_coordinates(depth=depth_map, intrinsic=intrinsic, extrinsic=extrinsic,
+                                                      depth_scale=1.0, depth_max=4.0, trunc_voxel_multiplier=10.0)
+        vbg.integrate(block_coords=coords, depth=depth_map, intrinsic=intrinsic, extrinsic=extrinsic,
+                      depth_scale=1.0, depth_max=4.0, trunc_voxel_multiplier=10.0)
+        keys = og.touch(depth_np, K[index], Ewc[index], 4.0, 10.0)
+        og.integrate(keys, depth_np, K[index], Ewc[index], 4.0, 10.0)
+    k0, t0, w0 = sort_blocks(*og.export()[:3])
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    mesh = vbg.extract_triangle_mesh(weight_threshold=1.5, estimated_vertex_number=-1)
+    legacy = mesh.to_legacy()
+    assert len(legacy.triangles) == len(og.extract_mesh(1.5)[2]) and legacy.vertices.dtype == np.float64
+    pcd = vbg.extract_point_cloud().to_legacy()
+    assert len(pcd.points) == len(og.extract_points(3.0)[0])
+    scene = o3d.t.geometry.RaycastingScene(device=device)
+    scene.add_triangles(mesh.cpu())
+    rays = scene.create_rays_pinhole(o3d.core.Tensor(K[0], dtype=o3d.core.Dtype.Float32),
+                                     o3d.core.Tensor(Ewc[0], dtype=o3d.core.Dtype.Float32), width_px=80, height_px=80)
+    depth = scene.cast_rays(rays)["t_hit"].cpu().numpy()
+    assert depth.shape == (80, 80)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        o3d.t.geometry.VoxelBlockGrid(voxel_size=0.02, block_count=10, device=o3d.core.Device("CPU:0"))

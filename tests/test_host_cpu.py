@@ -1,0 +1,103 @@
+"""CPU: host-side logic -- config parser, dataset containers, on-disk formats, synthetic project layout."""
+import os
+
+import numpy as np
+import pytest
+
+import mq3d_b200  # noqa: F401
+from mq3d_b200 import synth
+from mq3d_b200.config import PipelineConfigs, ReconstructionConfig
+from mq3d_b200.dataio import DESCRIPTOR_COLUMNS, DataIO, depth_camera_params
+from mq3d_b200.geometry import LegacyPointCloud, LegacyTriangleMesh
+from mq3d_b200.io_utils import read_ply, write_point_cloud, write_triangle_mesh
+from mq3d_b200.models import CameraDataset, ConfidenceMap, DepthDataset, Side
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parse_pipeline_config_yml():
+    cfg = PipelineConfigs.parse_config_yml(os.path.join(ROOT, "config", "pipeline_config.yml")).reconstruction
+    assert cfg.device == "CUDA:0" and cfg.depth_integration.device == "CUDA:0"
+    di = cfg.depth_integration
+    assert (di.voxel_size, di.block_resolution, di.block_count, di.depth_max, di.trunc_voxel_multiplier) == \
+        (0.01, 16, 50000, 4.0, 10.0)
+    assert (di.confidence_threshold, di.valid_count_threshold) == (0.02, 2)
+    assert cfg.confidence_estimation.target_frame_range == 10 and cfg.confidence_estimation.error_threshold == 0.08
+    assert cfg.color_optimization.weight_threshold == 1.5 and cfg.color_optimization.min_triangle_count == 5000
+    assert cfg.fragment_pose_refinement.relative_rmses == [1e-6, 1e-6, 1e-6]     # "1e-6" strings coerced
+    assert cfg.use_dataset_cache is False and cfg.color_optimization.use_dataset_cache is False
+
+
+def test_config_defaults_and_device_policy():
+    cfg = ReconstructionConfig.parse({})
+    assert cfg.depth_integration.depth_max == 1.5 and cfg.depth_integration.trunc_voxel_multiplier == 8.0
+    assert cfg.depth_integration.confidence_threshold == 0.05 and cfg.depth_integration.valid_count_threshold == 4
+    assert cfg.color_optimization.weight_threshold == 3.0
+    assert ReconstructionConfig.parse({"device": "CPU:0"}).device == "CUDA:0"         # remapped with a warning
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ReconstructionConfig.parse({"device": "CPU:0"}, allow_device_override=False)
+    assert ReconstructionConfig.parse({"device": "cuda:3", "depth_integration": {"voxel_size": "0.005"}}) \
+        .depth_integration.voxel_size == 0.005
+
+
+def test_dataset_roundtrip_and_indexing(tmp_path):
+    cap = synth.make_depth_capture(5, Side.LEFT, width=32, height=32)
+    ds = cap.dataset
+    p = tmp_path / "dataset" / "left_depth_dataset.npz"
+    ds.save(p)
+    ds2 = DepthDataset.load(p)
+    assert np.array_equal(ds2.timestamps, ds.timestamps) and np.array_equal(ds2.nears, ds.nears)
+    assert ds2.transforms.coordinate_system == ds.transforms.coordinate_system
+    assert np.array_equal(ds2.transforms.rotations, ds.transforms.rotations)
+    sub = ds[1:4]
+    assert len(sub) == 3 and isinstance(sub, DepthDataset) and sub.timestamps[0] == ds.timestamps[1]
+    assert [len(f) for f in ds.split(2)] == [2, 2, 1]
+    k = ds.get_intrinsic_matrices()
+    assert k.dtype == np.float32 and k[0, 0, 0] == 16.0 and k[0, 2, 2] == 1.0
+    cds = synth.make_color_dataset(3)
+    cds.save(tmp_path / "c.npz")
+    assert np.array_equal(CameraDataset.load(tmp_path / "c.npz").fx, cds.fx)
+    assert cds.fx.dtype.kind == "i"            # colour intrinsics are integer arrays
+
+
+def test_project_layout_and_descriptor_csv(tmp_path):
+    caps = synth.write_project(tmp_path, 3, width=32, height=32)
+    io = DataIO(tmp_path)
+    for side in Side:
+        ds = caps[side].dataset
+        header = (tmp_path / f"{side.value}_depth_descriptors.csv").read_text().splitlines()[0].split(",")
+        assert header == DESCRIPTOR_COLUMNS
+        raw = io.depth.load_raw_depth_map(side, ds.timestamps[1], 32, 32)
+        assert raw.dtype == np.float32 and np.array_equal(raw, caps[side].raw[1])
+        assert io.depth.load_raw_depth_map(side, 12345, 32, 32) is None
+    assert depth_camera_params(1.0, 1.0, 1.0, 1.0, 320, 320) == (160.0, 160.0, 160.0, 160.0)
+    cm = ConfidenceMap(np.random.rand(4, 6), np.ones((4, 6), np.int32))
+    io.depth.save_confidence_map(Side.LEFT, 77, cm)
+    back = io.depth.load_confidence_map(Side.LEFT, 77)
+    assert back.confidence_map.dtype == np.float64 and back.valid_count.dtype == np.int32
+    assert np.array_equal(back.confidence_map, cm.confidence_map)
+    assert io.depth.load_confidence_map(Side.LEFT, 78) is None
+    assert (tmp_path / "left_depth_confidence" / "77.npz").exists()
+    with pytest.raises(ValueError):
+        ConfidenceMap(np.zeros((2, 2)), np.zeros((3, 2), np.int32))
+
+
+def test_ply_roundtrip(tmp_path):
+    v = np.random.rand(10, 3)
+    n = np.random.rand(10, 3)
+    t = np.random.randint(0, 10, (7, 3)).astype(np.int32)
+    write_triangle_mesh(tmp_path / "m.ply", LegacyTriangleMesh(v, t, n))
+    vv, tt = read_ply(tmp_path / "m.ply")
+    assert np.array_equal(np.stack([vv["x"], vv["y"], vv["z"]], 1), v) and np.array_equal(tt, t)
+    assert np.array_equal(vv["nz"], n[:, 2])
+    write_point_cloud(tmp_path / "p.ply", LegacyPointCloud(v, n))
+    pv, pt = read_ply(tmp_path / "p.ply")
+    assert pt is None and np.array_equal(pv["y"], v[:, 1])
+
+
+def test_synthetic_capture_is_valid_quest_shaped():
+    cap = synth.make_depth_capture(300, Side.LEFT, width=16, height=16)
+    assert cap.raw.dtype == np.float32 and cap.raw.shape == (300, 16, 16)
+    assert (cap.raw >= 0).all() and (cap.raw <= 1).all()      # never closer than the near plane
+    assert 0.005 < (cap.raw == 1.0).mean() < 0.05              # ~2 % dropped pixels
+    assert np.array_equal(np.diff(cap.dataset.timestamps)[:3], [33, 34, 33])
