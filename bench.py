@@ -187,6 +187,9 @@ def run_gpu(args):
         e0.record()
         v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
         e1.record()
+        if world > 1:            # the north star's "final gather": per-rank meshes -> rank 0 over NCCL
+            from mq3d_b200.dist import gather_mesh
+            gather_mesh(v, nrm, t, dst=0)
         return st, (v, nrm, t), (e0, e1)
 
     # ---- device-resident timing -------------------------------------------------------------------
@@ -198,7 +201,9 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats, mc_events = [], []
     ev0.record()
+    mesh = None
     for _ in range(args.steps):
+        mesh = None          # release the previous step's mesh before the next one is allocated
         st, mesh, mce = step_device()
         stats.append(st)
         mc_events.append(mce)
@@ -206,7 +211,10 @@ def run_gpu(args):
     barrier()
     clocks = sampler.stop()
     total_ms = ev0.elapsed_time(ev1)
-    mc_ms = float(np.mean([a.elapsed_time(b) for a, b in mc_events]))
+    mc_list = [a.elapsed_time(b) for a, b in mc_events]
+    if os.environ.get("MQ3D_TRACE"):
+        print("[bench] per-step mc ms:", [round(x, 3) for x in mc_list], file=sys.stderr)
+    mc_ms = float(np.mean(mc_list))
     st = stats[-1]
     integ_ms = float(np.mean([s.integrate_ms for s in stats]))
     touch_ms = float(np.mean([s.touch_ms for s in stats]))

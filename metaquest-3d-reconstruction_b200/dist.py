@@ -1,0 +1,95 @@
+"""Multi-GPU plumbing: voxel blocks are partitioned by a spatial hash of their super-tile,
+every rank integrates the broadcast frames into the blocks it owns plus a one-block ghost shell
+(values are bit-identical to the owner's, so there is no halo exchange), meshes are extracted per
+rank for owned cubes only and gathered on rank 0.  torch.distributed (NCCL on the box, gloo in the
+CPU tests) carries exactly two things: the frame broadcast and this final gather.
+
+The Python functions below restate the device-side ownership rule (csrc/mq3d_common.cuh:
+mq3d_tile_owner / mq3d_block_needed) so that tests can check the partition without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+_BIAS = 1 << 20
+_M64 = (1 << 64) - 1
+
+
+def _hash64(k: int) -> int:
+    k &= _M64
+    k ^= k >> 33
+    k = (k * 0xFF51AFD7ED558CCD) & _M64
+    k ^= k >> 33
+    k = (k * 0xC4CEB9FE1A85EC53) & _M64
+    k ^= k >> 33
+    return k & 0xFFFFFFFF
+
+
+def _pack(x: int, y: int, z: int) -> int:
+    return (((x + _BIAS) & 0xFFFFFFFF) << 42) | (((y + _BIAS) & 0xFFFFFFFF) << 21) | ((z + _BIAS) & 0xFFFFFFFF)
+
+
+def tile_owner(bx: int, by: int, bz: int, world: int, tile_blocks: int = 8) -> int:
+    """Owner rank of the block (bx,by,bz): hash of its super-tile modulo the world size."""
+    s = tile_blocks.bit_length() - 1
+    return _hash64(_pack(bx >> s, by >> s, bz >> s)) % world
+
+
+def block_needed(bx: int, by: int, bz: int, rank: int, world: int, tile_blocks: int = 8) -> bool:
+    """True when the block is owned by `rank` or lies in the one-block shell around an owned tile."""
+    if world <= 1:
+        return True
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if tile_owner(bx + dx, by + dy, bz + dz, world, tile_blocks) == rank:
+                    return True
+    return False
+
+
+def broadcast_frames(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """Frame broadcast (raw depth / colour batches) from `src` to every rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src)
+    return t
+
+
+def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangles: torch.Tensor, dst: int = 0):
+    """Concatenate per-rank meshes on `dst`: vertex arrays are appended in rank order and triangle
+    indices rebased by the exclusive scan of the per-rank vertex counts.  Returns (vertices, normals,
+    triangles, counts [world,2]) on dst and (None, None, None, counts) elsewhere.  Vertices on edges owned
+    by ghost blocks are emitted by every rank that references them (no welding)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        counts = torch.tensor([[vertices.shape[0], triangles.shape[0]]], dtype=torch.int64)
+        return vertices, normals, triangles, counts
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = vertices.device
+    mine = torch.tensor([vertices.shape[0], triangles.shape[0]], dtype=torch.int64, device=dev)
+    counts = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine) if dev.type == "cuda" else dist.all_gather(list(counts.unbind(0)), mine)
+    counts_h = counts.cpu()
+    vmax, tmax = int(counts_h[:, 0].max()), int(counts_h[:, 1].max())
+
+    def padded(x, n, dtype):
+        out = torch.zeros((n, 3), dtype=dtype, device=dev)
+        if x is not None and x.shape[0]:
+            out[: x.shape[0]] = x
+        return out
+
+    send = [padded(vertices, vmax, torch.float32), padded(normals, vmax, torch.float32),
+            padded(triangles, tmax, torch.int32)]
+    recv = [[torch.empty_like(s) for _ in range(world)] if rank == dst else None for s in send]
+    for s, r in zip(send, recv):
+        dist.gather(s, r, dst=dst)
+    if rank != dst:
+        return None, None, None, counts_h
+    voff = torch.cumsum(counts_h[:, 0], 0) - counts_h[:, 0]
+    v = torch.cat([recv[0][r][: int(counts_h[r, 0])] for r in range(world)])
+    n = torch.cat([recv[1][r][: int(counts_h[r, 0])] for r in range(world)]) if normals is not None else None
+    t = torch.cat([recv[2][r][: int(counts_h[r, 1])] + int(voff[r]) for r in range(world)])
+    return v, n, t, counts_h

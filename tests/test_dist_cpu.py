@@ -1,0 +1,64 @@
+"""CPU: the N>1 host path on the gloo backend (world_size 2) -- frame broadcast + final mesh gather --
+and the ownership rule of the hash partition."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+import mq3d_b200  # noqa: F401
+from mq3d_b200.dist import block_needed, tile_owner
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200.dist import broadcast_frames, gather_mesh
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) if rank == 0 else torch.zeros(2, 3, 4)
+    broadcast_frames(frames, 0)
+    assert torch.equal(frames, torch.arange(24, dtype=torch.float32).reshape(2, 3, 4))
+    nv = 3 + 2 * rank                                     # ragged sizes; rank 1 also tests a non-empty tail
+    v = torch.full((nv, 3), float(rank)) + torch.arange(nv)[:, None]
+    n = -v
+    t = torch.tensor([[0, 1, 2]] * (1 + rank), dtype=torch.int32)
+    gv, gn, gt, counts = gather_mesh(v, n, t, dst=0)
+    assert counts.tolist() == [[3, 1], [5, 2]]
+    if rank == 0:
+        assert gv.shape == (8, 3) and gt.shape == (3, 3)
+        assert gt.tolist() == [[0, 1, 2], [3, 4, 5], [3, 4, 5]]          # rank-1 indices rebased by 3
+        assert torch.equal(gv[3:], torch.full((5, 3), 1.0) + torch.arange(5)[:, None]) and torch.equal(gn, -gv)
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert gv is None and gt is None
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_gather_world2(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_partition_ownership_rule():
+    world, T = 4, 4
+    keys = [(x, y, z) for x in range(-9, 9) for y in range(-3, 5) for z in range(-6, 7)]
+    owners = np.array([tile_owner(*k, world, T) for k in keys])
+    assert set(owners.tolist()) == {0, 1, 2, 3}                        # every rank owns something
+    assert np.bincount(owners).min() > 0.1 * len(keys)                 # no rank starves
+    for k in keys[::17]:
+        o = tile_owner(*k, world, T)
+        assert tile_owner(k[0] - k[0] % T, k[1] - k[1] % T, k[2] - k[2] % T, world, T) == o   # tile-constant
+        needed = [r for r in range(world) if block_needed(*k, r, world, T)]
+        assert o in needed
+        nb_owners = {tile_owner(k[0] + dx, k[1] + dy, k[2] + dz, world, T)
+                     for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)}
+        assert set(needed) == nb_owners                                # ghost shell = owners of the 26 neighbours
+    assert block_needed(1, 2, 3, 0, 1, T)                              # world 1: everything is local
