@@ -213,6 +213,7 @@ struct mq3d_grid {
     int32_t *idx_scratch;  // per-frame integrate: block index per key
     int64_t idx_scratch_size;
     int *pinned_host;     // pinned int[8] for async readbacks
+    int64_t *pinned_host64;            // two pinned int64 (tail of pinned_host) for the MC totals
     int *frame_counts_dev;             // [MQ3D_MAX_BATCH]
     unsigned long long *stat_dev;      // [2]
     cudaEvent_t *events;               // persistent timing events of the sequence path

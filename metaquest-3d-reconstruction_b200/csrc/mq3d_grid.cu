@@ -133,7 +133,8 @@ extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t 
             MQ3D_CUDA(cudaMalloc(&g->counter_dev, sizeof(int) * 8));
             MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * 8, st));
             MQ3D_CUDA(cudaMalloc(&g->frame_params_dev, sizeof(FrameParams) * MQ3D_MAX_BATCH));
-            MQ3D_CUDA(cudaMallocHost(&g->pinned_host, sizeof(int) * 8));
+            MQ3D_CUDA(cudaMallocHost(&g->pinned_host, sizeof(int) * 16));
+            g->pinned_host64 = reinterpret_cast<int64_t *>(g->pinned_host + 8);
             MQ3D_CUDA(cudaMalloc(&g->frame_counts_dev, sizeof(int) * MQ3D_MAX_BATCH));
             MQ3D_CUDA(cudaMalloc(&g->stat_dev, sizeof(unsigned long long) * 2));
             return MQ3D_OK;

@@ -5,23 +5,33 @@
 // (reference: processing/reconstruction/reconstruct_scene.py:90,105-108,186-189).
 //
 // GPU formulation (no global 16 B/voxel "mesh_structure" volume, no global atomics):
-//   classify (one CTA per block): stage validity/sign bits of the (-1..16)^3 neighbourhood in shared
-//     memory, derive the cube case of every cube in (-1..15)^3, mark the lattice edges the block owns
-//     with warp ballots (3 bit-planes x 128 words), popcount them, and keep per-word prefix counts so
-//     that  id(voxel, axis) = vertex_offset[block] + prefix[word] + popc(mask[word] & lower_lanes)
+//   classify (one CTA per block): the validity (exists && w > thr) and sign (tsdf < 0) of the
+//     (-1..16)^3 neighbourhood are reduced to 18-bit ROWS along x while they are loaded (float4 for
+//     the 16-voxel interior of a row).  Everything else is row-wise bit arithmetic: cube validity
+//     = AND of four rows and their shift, "surface" cubes = valid cubes whose 8 signs differ, edge
+//     marks = sign difference AND (OR of the four cubes sharing the edge).  Per block it stores
+//     16-bit edge-mark rows for the three axes, their exclusive prefix counts, the surface-cube rows,
+//     triangle prefix counts and the sign rows (5.4 KB), so that
+//       id(voxel, axis) = vertex_offset[block] + prefix[axis][z,y] + popc(mask[axis][z,y] & below(x))
 //     is computable by any neighbour without a lookup table;
 //   scan: exclusive prefix of per-block vertex / triangle counts;
-//   emit (one CTA per non-empty block): stage the (-1..17)^3 tsdf neighbourhood, write vertices and
-//     normals at their scanned positions and triangles with ids resolved through the bit-planes.
+//   emit (one CTA per non-empty block): one thread per (axis, row) walks its marked edges and writes
+//     vertices + normals (tsdf read straight from global/L2: ~14 values per vertex), one thread per
+//     cube row walks its surface cubes and writes triangles with ids resolved through the bit rows.
 // Output order is deterministic.  A cube counts on this rank only if its block is owned (multi-GPU
 // partition); single-GPU grids own every block.
 #include "mc_tables.h"
 #include "mq3d_common.cuh"
 
-#define CODE_R 18   // validity/sign region: coords -1..16
-#define CUBE_R 17   // cube region: coords -1..15
-#define TS_R 19     // tsdf region: coords -1..17
-#define EWORDS 384  // 3 planes x 128 words
+#define TS_R 19      // tsdf region of the point-cloud kernel: coords -1..17
+#define ROW_R 18     // validity / sign rows: (y,z) in -1..16, bit i <-> x = i - 1
+#define SROW_WORDS (ROW_R * ROW_R)
+// per-block uint16 table
+#define R16_EMASK 0      // [3][256] edge marks, bit x
+#define R16_EPREF 768    // [3][256] exclusive prefix of popc(edge marks) in (axis, z, y) order
+#define R16_SURF 1536    // [256]    surface cubes of the own rows, bit x
+#define R16_TPREF 1792   // [256]    exclusive prefix of per-row triangle counts
+#define R16_WORDS 2048
 
 __device__ __forceinline__ int nb_of(int r) { return r < 0 ? 0 : (r > 15 ? 2 : 1); }  // -> d+1
 
@@ -43,7 +53,7 @@ __global__ void k_mc_neighbors(HashView h, const int32_t *__restrict__ block_key
     nb[i] = r;
 }
 
-// exclusive scan of 128 or 384 small counts held in shared memory, by warp 0 (n % 32 == 0)
+// exclusive scan of n (multiple of 32) small counts held in shared memory, by warp 0; returns total
 __device__ __forceinline__ int warp0_exclusive_scan(int *s, int n, int lane) {
     const int per = n / 32;
     int sum = 0;
@@ -59,23 +69,32 @@ __device__ __forceinline__ int warp0_exclusive_scan(int *s, int n, int lane) {
         s[lane * per + i] = run;
         run += c;
     }
-    return __shfl_sync(0xFFFFFFFFu, incl, 31);  // total
+    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+
+// cube case (Bourke corner order) of the cube whose low corner is bit i of rows (y,z):
+// s00 = (y,z), s10 = (y+1,z), s01 = (y,z+1), s11 = (y+1,z+1)
+__device__ __forceinline__ int cube_case(unsigned s00, unsigned s10, unsigned s01, unsigned s11, int i) {
+    unsigned a = (s00 >> i) & 3u, b = (s10 >> i) & 3u, c = (s01 >> i) & 3u, d = (s11 >> i) & 3u;
+    // corners 0:(0,0,0) 1:(1,0,0) 2:(1,1,0) 3:(0,1,0) 4:(0,0,1) 5:(1,0,1) 6:(1,1,1) 7:(0,1,1)
+    return (int)((a & 1u) | (a & 2u) | ((b & 2u) << 1) | ((b & 1u) << 3) | ((c & 1u) << 4) | ((c & 2u) << 4) |
+                 ((d & 2u) << 5) | ((d & 1u) << 7));
 }
 
 // ------------------------------------------------------------------------------------------------
 // classify
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, const int32_t *__restrict__ block_keys,
-              const int32_t *__restrict__ nb, float weight_thr, Partition part, uint32_t *__restrict__ emask,
-              uint16_t *__restrict__ eprefix, uint8_t *__restrict__ cubes, int32_t *__restrict__ counts) {
-    __shared__ uint8_t s_code[CODE_R * CODE_R * CODE_R];
-    __shared__ uint8_t s_cube[CUBE_R * CUBE_R * CUBE_R];
+              const int32_t *__restrict__ nb, float weight_thr, Partition part, uint32_t *__restrict__ srow_out,
+              uint16_t *__restrict__ rows16, int32_t *__restrict__ counts) {
+    __shared__ unsigned s_valid[SROW_WORDS], s_sign[SROW_WORDS];
+    __shared__ unsigned s_cok[17 * 17];
     __shared__ int s_nb[27];
-    __shared__ uint8_t s_owned[27];
-    __shared__ uint8_t s_tric[256];
-    __shared__ int s_cnt[EWORDS];
-    __shared__ int s_tri[8];
+    __shared__ unsigned char s_owned[27];
+    __shared__ unsigned char s_tric[256];
+    __shared__ int s_ecnt[768];
+    __shared__ int s_tcnt[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
     if (tid < 27) {
@@ -84,79 +103,115 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
         s_owned[tid] = mq3d_block_owned(block_keys[3 * b] + dx, block_keys[3 * b + 1] + dy, block_keys[3 * b + 2] + dz, part);
     }
     s_tric[tid] = MC_TRI_COUNT[tid];
-    __syncthreads();
-    // stage validity + sign bits of the (-1..16)^3 neighbourhood
-    for (int r = tid; r < CODE_R * CODE_R * CODE_R; r += 256) {
-        int rx = r % CODE_R - 1, ry = (r / CODE_R) % CODE_R - 1, rz = r / (CODE_R * CODE_R) - 1;
-        int k = nb_of(rx) + 3 * nb_of(ry) + 9 * nb_of(rz);
-        int bi = s_nb[k];
-        uint8_t code = 0;
-        if (bi >= 0) {
-            int64_t li = (int64_t)bi * MQ3D_RES3 + (((rz & 15) * 16 + (ry & 15)) * 16 + (rx & 15));
-            float t = __ldg(tsdf + li), w = __ldg(weight + li);
-            code = (w > weight_thr ? 1 : 0) | (t < 0.0f ? 2 : 0);   // reject is `w <= thr`
-        }
-        s_code[r] = code;
+    for (int i = tid; i < SROW_WORDS; i += 256) {
+        s_valid[i] = 0;
+        s_sign[i] = 0;
     }
     __syncthreads();
-    // cube cases for cubes in (-1..15)^3
-    for (int c = tid; c < CUBE_R * CUBE_R * CUBE_R; c += 256) {
-        int cx = c % CUBE_R, cy = (c / CUBE_R) % CUBE_R, cz = c / (CUBE_R * CUBE_R);  // region coords (cube -1 -> 0)
-        int valid = 1, table = 0;
+    // ---- phase A: load the neighbourhood as bit rows (6 segments per row: x=-1 | 4 x float4 | x=16) ----
+    // Every item is one float4 of tsdf and one of weight (the x=-1 / x=16 columns use the last / first
+    // quad of the neighbour's row); the loop is branch-free up to the shared-memory ORs so that ptxas
+    // keeps the 8 128-bit loads of a round in flight (two rounds of 4 items bound the registers).
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        constexpr int N_IT = 4;
+        static_assert(2 * N_IT * 256 >= SROW_WORDS * 6, "phase A does not cover the neighbourhood");
+        float4 tq[N_IT], wq[N_IT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int code = s_code[((cz + MC_VTX_SHIFTS[i][2]) * CODE_R + cy + MC_VTX_SHIFTS[i][1]) * CODE_R + cx + MC_VTX_SHIFTS[i][0]];
-            valid &= code;
-            table |= ((code >> 1) & 1) << i;
+        for (int k = 0; k < N_IT; ++k) {
+            const int it = tid + 256 * (k + N_IT * round);
+            const int r = min(it / 6, SROW_WORDS - 1), seg = it % 6;
+            const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
+            const int nbx = seg == 0 ? 0 : (seg == 5 ? 2 : 1);
+            const int bi = s_nb[nbx + 3 * nb_of(ry) + 9 * nb_of(rz)];
+            const int quad = seg == 0 ? 3 : (seg == 5 ? 0 : seg - 1);
+            // missing neighbour / tail item: read this block's own row instead (result is discarded)
+            const int64_t base = (int64_t)(bi < 0 ? (int)b : bi) * MQ3D_RES3 + ((rz & 15) * 16 + (ry & 15)) * 16;
+            tq[k] = __ldg(reinterpret_cast<const float4 *>(tsdf + base) + quad);
+            wq[k] = __ldg(reinterpret_cast<const float4 *>(weight + base) + quad);
         }
-        int k = nb_of(cx - 1) + 3 * nb_of(cy - 1) + 9 * nb_of(cz - 1);
-        s_cube[c] = (valid & 1) && s_owned[k] ? (uint8_t)table : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < N_IT; ++k) {
+            const int it = tid + 256 * (k + N_IT * round);
+            const int r = min(it / 6, SROW_WORDS - 1), seg = it % 6;
+            const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
+            const int nbx = seg == 0 ? 0 : (seg == 5 ? 2 : 1);
+            const bool live = it < SROW_WORDS * 6 && s_nb[nbx + 3 * nb_of(ry) + 9 * nb_of(rz)] >= 0;
+            const float4 t = tq[k], w = wq[k];
+            // Open3D rejects `w <= thr`
+            unsigned v4 = (w.x > weight_thr ? 1u : 0u) | (w.y > weight_thr ? 2u : 0u) | (w.z > weight_thr ? 4u : 0u) |
+                          (w.w > weight_thr ? 8u : 0u);
+            unsigned s4 = (t.x < 0.0f ? 1u : 0u) | (t.y < 0.0f ? 2u : 0u) | (t.z < 0.0f ? 4u : 0u) | (t.w < 0.0f ? 8u : 0u);
+            unsigned vb, sb;
+            if (seg == 0) { vb = v4 >> 3; sb = s4 >> 3; }                              // x = -1  -> bit 0
+            else if (seg == 5) { vb = (v4 & 1u) << 17; sb = (s4 & 1u) << 17; }          // x = 16  -> bit 17
+            else { vb = v4 << (4 * seg - 3); sb = s4 << (4 * seg - 3); }                // x = 4(seg-1).. -> bits 1+..
+            if (live && vb) atomicOr(&s_valid[r], vb);
+            if (live && sb) atomicOr(&s_sign[r], sb);
+        }
     }
     __syncthreads();
-    // edge marks of the voxels this block owns + own-cube triangle counts
-    int tri_local = 0;
-    for (int it = 0; it < 16; ++it) {
-        int v = it * 256 + tid;
-        int x = v & 15, y = (v >> 4) & 15, z = v >> 8;
-        int so = (s_code[((z + 1) * CODE_R + y + 1) * CODE_R + x + 1] >> 1) & 1;
-        int sx = (s_code[((z + 1) * CODE_R + y + 1) * CODE_R + x + 2] >> 1) & 1;
-        int sy = (s_code[((z + 1) * CODE_R + y + 2) * CODE_R + x + 1] >> 1) & 1;
-        int sz = (s_code[((z + 2) * CODE_R + y + 1) * CODE_R + x + 1] >> 1) & 1;
-        // cubes sharing each edge (cube region index: coord + 1)
-#define CUBE(ix, iy, iz) s_cube[(((iz) + 1) * CUBE_R + (iy) + 1) * CUBE_R + (ix) + 1]
-        int c000 = CUBE(x, y, z);
-        int mx = (so != sx) && (c000 | CUBE(x, y - 1, z) | CUBE(x, y, z - 1) | CUBE(x, y - 1, z - 1));
-        int my = (so != sy) && (c000 | CUBE(x - 1, y, z) | CUBE(x, y, z - 1) | CUBE(x - 1, y, z - 1));
-        int mz = (so != sz) && (c000 | CUBE(x - 1, y, z) | CUBE(x, y - 1, z) | CUBE(x - 1, y - 1, z));
-#undef CUBE
-        unsigned bx_ = __ballot_sync(0xFFFFFFFFu, mx), by_ = __ballot_sync(0xFFFFFFFFu, my),
-                 bz_ = __ballot_sync(0xFFFFFFFFu, mz);
-        int word = it * 8 + warp;
-        if (lane == 0) {
-            emask[b * EWORDS + word] = bx_;
-            emask[b * EWORDS + 128 + word] = by_;
-            emask[b * EWORDS + 256 + word] = bz_;
-            s_cnt[word] = __popc(bx_);
-            s_cnt[128 + word] = __popc(by_);
-            s_cnt[256 + word] = __popc(bz_);
-        }
-        cubes[b * MQ3D_RES3 + v] = (uint8_t)c000;
-        tri_local += s_tric[c000];
+    // ---- phase B: valid (and owned) cubes of the cube rows (cy,cz) in -1..15, bit i <-> cube x = i-1 ----
+    for (int c = tid; c < 17 * 17; c += 256) {
+        const int cy = c % 17, cz = c / 17;      // region row index of the cube's low corner (cube y = cy-1)
+        const unsigned m = s_valid[cz * ROW_R + cy] & s_valid[cz * ROW_R + cy + 1] & s_valid[(cz + 1) * ROW_R + cy] &
+                           s_valid[(cz + 1) * ROW_R + cy + 1];
+        unsigned ok = m & (m >> 1) & 0x1FFFFu;
+        const int ky = cy == 0 ? 0 : 1, kz = cz == 0 ? 0 : 1;     // cube y/z = -1 -> neighbour block -1
+        const unsigned own = (s_owned[0 + 3 * ky + 9 * kz] ? 1u : 0u) | (s_owned[1 + 3 * ky + 9 * kz] ? 0x1FFFEu : 0u);
+        s_cok[c] = ok & own;
     }
-    for (int o = 16; o > 0; o >>= 1) tri_local += __shfl_xor_sync(0xFFFFFFFFu, tri_local, o);
-    if (lane == 0) s_tri[warp] = tri_local;
+    __syncthreads();
+    // ---- phase C: one thread per own row (y,z): edge marks, surface cubes, triangle count ----
+    {
+        const int y = tid & 15, z = tid >> 4;
+        const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
+        const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
+        // cube rows (index = cube coord + 1): (y,z) (y-1,z) (y,z-1) (y-1,z-1)
+        const unsigned c00 = s_cok[(z + 1) * 17 + y + 1], cm0 = s_cok[(z + 1) * 17 + y];
+        const unsigned c0m = s_cok[z * 17 + y + 1], cmm = s_cok[z * 17 + y];
+        const unsigned ex = (s00 ^ (s00 >> 1)) & (c00 | cm0 | c0m | cmm);
+        const unsigned cy_ = c00 | c0m, cz_ = c00 | cm0;
+        const unsigned ey = (s00 ^ s10) & (cy_ | (cy_ << 1));
+        const unsigned ez = (s00 ^ s01) & (cz_ | (cz_ << 1));
+        const unsigned mx = (ex >> 1) & 0xFFFFu, my = (ey >> 1) & 0xFFFFu, mz = (ez >> 1) & 0xFFFFu;
+        // surface cubes of this row: valid cubes whose 8 corner signs are not all equal
+        const unsigned same4 = ~((s00 ^ s10) | (s00 ^ s01) | (s00 ^ s11));
+        const unsigned flat = same4 & (same4 >> 1) & ~(s00 ^ (s00 >> 1));
+        unsigned surf = (c00 & ~flat) >> 1 & 0xFFFFu;
+        int ntri = 0;
+        for (unsigned m = surf; m; m &= m - 1) {
+            const int x = __ffs(m) - 1;
+            ntri += s_tric[cube_case(s00, s10, s01, s11, x + 1)];
+        }
+        uint16_t *r16 = rows16 + b * R16_WORDS;
+        r16[R16_EMASK + tid] = (uint16_t)mx;
+        r16[R16_EMASK + 256 + tid] = (uint16_t)my;
+        r16[R16_EMASK + 512 + tid] = (uint16_t)mz;
+        r16[R16_SURF + tid] = (uint16_t)surf;
+        s_ecnt[tid] = __popc(mx);
+        s_ecnt[256 + tid] = __popc(my);
+        s_ecnt[512 + tid] = __popc(mz);
+        s_tcnt[tid] = ntri;
+    }
     __syncthreads();
     if (warp == 0) {
-        int total = warp0_exclusive_scan(s_cnt, EWORDS, lane);
+        const int nv = warp0_exclusive_scan(s_ecnt, 768, lane);
+        const int nt = warp0_exclusive_scan(s_tcnt, 256, lane);
         if (lane == 0) {
-            int t = 0;
-            for (int i = 0; i < 8; ++i) t += s_tri[i];
-            counts[2 * b] = total;
-            counts[2 * b + 1] = t;
+            counts[2 * b] = nv;
+            counts[2 * b + 1] = nt;
         }
     }
     __syncthreads();
-    for (int i = tid; i < EWORDS; i += 256) eprefix[b * EWORDS + i] = (uint16_t)s_cnt[i];
+    {
+        uint16_t *r16 = rows16 + b * R16_WORDS;
+        r16[R16_EPREF + tid] = (uint16_t)s_ecnt[tid];
+        r16[R16_EPREF + 256 + tid] = (uint16_t)s_ecnt[256 + tid];
+        r16[R16_EPREF + 512 + tid] = (uint16_t)s_ecnt[512 + tid];
+        r16[R16_TPREF + tid] = (uint16_t)s_tcnt[tid];
+        for (int i = tid; i < SROW_WORDS; i += 256) srow_out[b * SROW_WORDS + i] = s_sign[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -168,9 +223,22 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t *__restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry[0] = s_carry[1] = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024) {
-        int64_t i = base + tid;
-        long long a = i < n ? counts[2 * i] : 0, c = i < n ? counts[2 * i + 1] : 0;
+    constexpr int PER = 8;   // consecutive blocks per thread: 8192 blocks per sweep
+    for (int64_t base = 0; base < n; base += 1024 * PER) {
+        const int64_t i0 = base + (int64_t)tid * PER;
+        long long a = 0, c = 0;
+        long long la[PER], lc[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int64_t i = i0 + q;
+            la[q] = a;
+            lc[q] = c;
+            if (i < n) {
+                const int2 v = __ldg(reinterpret_cast<const int2 *>(counts) + i);
+                a += v.x;
+                c += v.y;
+            }
+        }
         long long ia = a, ic = c;
         for (int o = 1; o < 32; o <<= 1) {
             long long ta = __shfl_up_sync(0xFFFFFFFFu, ia, o), tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
@@ -190,9 +258,14 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t *__restrict_
         }
         __syncthreads();
         long long ca = s_carry[0], cb = s_carry[1];
-        if (i < n) {
-            offsets[2 * i] = ca + s_a[warp] + ia - a;
-            offsets[2 * i + 1] = cb + s_b[warp] + ic - c;
+        const long long ta = ca + s_a[warp] + ia - a, tb = cb + s_b[warp] + ic - c;   // exclusive prefix of this thread
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int64_t i = i0 + q;
+            if (i < n) {
+                offsets[2 * i] = ta + la[q];
+                offsets[2 * i + 1] = tb + lc[q];
+            }
         }
         __syncthreads();
         if (tid == 1023) { s_carry[0] = ca + s_a[warp] + ia; s_carry[1] = cb + s_b[warp] + ic; }
@@ -202,27 +275,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared staging of the (-1..17)^3 tsdf neighbourhood
+// vertex writer shared by mesh and point cloud
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_tsdf(const float *__restrict__ tsdf, const int *s_nb, float *s_t, int tid) {
-    for (int r = tid; r < TS_R * TS_R * TS_R; r += 256) {
-        int rx = r % TS_R - 1, ry = (r / TS_R) % TS_R - 1, rz = r / (TS_R * TS_R) - 1;
-        int bi = s_nb[nb_of(rx) + 3 * nb_of(ry) + 9 * nb_of(rz)];
-        float t = 0.0f;
-        if (bi >= 0) t = __ldg(tsdf + (int64_t)bi * MQ3D_RES3 + (((rz & 15) * 16 + (ry & 15)) * 16 + (rx & 15)));
-        s_t[r] = t;
-    }
-}
-#define TS(ix, iy, iz) s_t[(((iz) + 1) * TS_R + (iy) + 1) * TS_R + (ix) + 1]
-#define EXISTS(ix, iy, iz) (s_nb[nb_of(ix) + 3 * nb_of(iy) + 9 * nb_of(iz)] >= 0)
-
-// DeviceGetNormal: central differences where both neighbours exist; other components untouched
-__device__ __forceinline__ void get_normal(const float *s_t, const int *s_nb, int x, int y, int z, float *n) {
-    if (EXISTS(x + 1, y, z) && EXISTS(x - 1, y, z)) n[0] = __fsub_rn(TS(x + 1, y, z), TS(x - 1, y, z));
-    if (EXISTS(x, y + 1, z) && EXISTS(x, y - 1, z)) n[1] = __fsub_rn(TS(x, y + 1, z), TS(x, y - 1, z));
-    if (EXISTS(x, y, z + 1) && EXISTS(x, y, z - 1)) n[2] = __fsub_rn(TS(x, y, z + 1), TS(x, y, z - 1));
-}
-
 __device__ __forceinline__ void write_vertex(float *__restrict__ verts, float *__restrict__ normals, int32_t *__restrict__ vkeys,
                                              int64_t id, float vs, int gx, int gy, int gz, int e, float ratio,
                                              const float *no, const float *ne) {
@@ -247,103 +301,133 @@ __device__ __forceinline__ void write_vertex(float *__restrict__ verts, float *_
     }
 }
 
+// voxel (x,y,z) relative to the block (coords -1..17) -> linear pool index, -1 if its block is missing
+__device__ __forceinline__ int64_t nb_lin(const int *s_nb, int x, int y, int z) {
+    const int bi = s_nb[nb_of(x) + 3 * nb_of(y) + 9 * nb_of(z)];
+    return bi < 0 ? -1 : (int64_t)bi * MQ3D_RES3 + (((z & 15) * 16 + (y & 15)) * 16 + (x & 15));
+}
+
+// DeviceGetNormal on global memory: central differences where both neighbours exist; other components
+// keep their previous value (Open3D's caller-visible stale behaviour)
+__device__ __forceinline__ void get_normal_g(const float *__restrict__ tsdf, const int *s_nb, int x, int y, int z, float *n) {
+    int64_t p, m;
+    p = nb_lin(s_nb, x + 1, y, z); m = nb_lin(s_nb, x - 1, y, z);
+    if (p >= 0 && m >= 0) n[0] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
+    p = nb_lin(s_nb, x, y + 1, z); m = nb_lin(s_nb, x, y - 1, z);
+    if (p >= 0 && m >= 0) n[1] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
+    p = nb_lin(s_nb, x, y, z + 1); m = nb_lin(s_nb, x, y, z - 1);
+    if (p >= 0 && m >= 0) n[2] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
+}
+
 // ------------------------------------------------------------------------------------------------
 // emit
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys, const int32_t *__restrict__ nb,
-          const uint32_t *__restrict__ emask, const uint16_t *__restrict__ eprefix, const uint8_t *__restrict__ cubes,
-          const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets, float vs,
-          float *__restrict__ verts, float *__restrict__ normals, int32_t *__restrict__ tris, int32_t *__restrict__ vkeys) {
-    __shared__ float s_t[TS_R * TS_R * TS_R];
+          const uint32_t *__restrict__ srow, const uint16_t *__restrict__ rows16, const int32_t *__restrict__ counts,
+          const int64_t *__restrict__ offsets, float vs, float *__restrict__ verts, float *__restrict__ normals,
+          int32_t *__restrict__ tris, int32_t *__restrict__ vkeys) {
     __shared__ int s_nb[27];
-    __shared__ uint32_t s_mask[EWORDS];
-    __shared__ uint16_t s_pref[EWORDS];
-    __shared__ int s_tsum[128];
+    __shared__ __align__(16) uint16_t s_r16[R16_WORDS];
+    __shared__ unsigned s_sign[SROW_WORDS];
     __shared__ signed char s_tt[256 * 16];
-    __shared__ uint8_t s_tric[256];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     const int nv = counts[2 * b], nt = counts[2 * b + 1];
     if (nv == 0 && nt == 0) return;
     if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
-    for (int i = tid; i < EWORDS; i += 256) {
-        s_mask[i] = emask[b * EWORDS + i];
-        s_pref[i] = eprefix[b * EWORDS + i];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows16 + b * R16_WORDS);
+        reinterpret_cast<uint4 *>(s_r16)[tid] = __ldg(src + tid);       // 256 x 16 B = 4 KB
     }
-    for (int i = tid; i < 256 * 16; i += 256) s_tt[i] = MC_TRI_TABLE[i >> 4][i & 15];
-    s_tric[tid] = MC_TRI_COUNT[tid];
+    const bool do_tris = nt > 0 && tris != nullptr;
+    if (do_tris) {
+        for (int i = tid; i < SROW_WORDS; i += 256) s_sign[i] = srow[b * SROW_WORDS + i];
+        for (int i = tid; i < 256 * 16; i += 256) s_tt[i] = MC_TRI_TABLE[i >> 4][i & 15];
+    }
     __syncthreads();
     const int kx = block_keys[3 * b], ky = block_keys[3 * b + 1], kz = block_keys[3 * b + 2];
     const int64_t voff = offsets[2 * b], toff = offsets[2 * b + 1];
+    // ---- vertices: one thread per vertex; (axis,row) by binary search in the prefix table, x = k-th set bit ----
     if (nv > 0) {
-        stage_tsdf(tsdf, s_nb, s_t, tid);
-        __syncthreads();
-        for (int it = 0; it < 16; ++it) {
-            int v = it * 256 + tid;
-            int word = v >> 5;
-            unsigned low = (1u << (v & 31)) - 1u, bit = 1u << (v & 31);
-            unsigned m0 = s_mask[word], m1 = s_mask[128 + word], m2 = s_mask[256 + word];
-            if (!((m0 | m1 | m2) & bit)) continue;
-            int x = v & 15, y = (v >> 4) & 15, z = v >> 8;
-            float to = TS(x, y, z);
-            float no[3] = {0.0f, 0.0f, 0.0f}, ne[3] = {0.0f, 0.0f, 0.0f};
-            get_normal(s_t, s_nb, x, y, z, no);
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                unsigned m = e == 0 ? m0 : (e == 1 ? m1 : m2);
-                if (!(m & bit)) continue;
-                int ex = x + (e == 0), ey = y + (e == 1), ez = z + (e == 2);
-                float te = TS(ex, ey, ez);
-                float ratio = __fdiv_rn(__fsub_rn(0.0f, to), __fsub_rn(te, to));
-                int64_t id = voff + s_pref[e * 128 + word] + __popc(m & low);
-                get_normal(s_t, s_nb, ex, ey, ez, ne);   // stale components persist across e (Open3D)
+        for (int j = tid; j < nv; j += 256) {
+            int lo = 0, hi = 767;                      // largest item with prefix <= j and a non-empty mask
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((int)s_r16[R16_EPREF + mid] <= j) lo = mid; else hi = mid - 1;
+            }
+            const int item = lo;
+            const unsigned m = s_r16[R16_EMASK + item];
+            const int e = item >> 8, row = item & 255, y = row & 15, z = row >> 4;
+            const int64_t id = voff + j;
+            {
+                const int x = (int)__fns(m, 0, j - (int)s_r16[R16_EPREF + item] + 1);
+                const int ex = x + (e == 0), ey = y + (e == 1), ez = z + (e == 2);
+                const float to = __ldg(tsdf + b * MQ3D_RES3 + row * 16 + x);
+                const float te = __ldg(tsdf + nb_lin(s_nb, ex, ey, ez));
+                const float ratio = __fdiv_rn(__fsub_rn(0.0f, to), __fsub_rn(te, to));
+                // Open3D keeps `ne` across the three edges of a voxel: components that cannot be
+                // recomputed at a later edge retain the value of the previous marked edge
+                float no[3] = {0.0f, 0.0f, 0.0f}, ne[3] = {0.0f, 0.0f, 0.0f};
+                get_normal_g(tsdf, s_nb, x, y, z, no);
+                for (int p = 0; p < e; ++p)
+                    if ((s_r16[R16_EMASK + p * 256 + row] >> x) & 1u)
+                        get_normal_g(tsdf, s_nb, x + (p == 0), y + (p == 1), z, ne);
+                get_normal_g(tsdf, s_nb, ex, ey, ez, ne);
                 write_vertex(verts, normals, vkeys, id, vs, kx * 16 + x, ky * 16 + y, kz * 16 + z, e, ratio, no, ne);
             }
         }
     }
-    if (nt > 0 && tris) {
-        // exclusive scan of per-cube triangle counts in voxel order
-        int cube[16];
-        for (int it = 0; it < 16; ++it) {
-            cube[it] = cubes[b * MQ3D_RES3 + it * 256 + tid];
-            int n = s_tric[cube[it]];
-            for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
-            if (lane == 0) s_tsum[it * 8 + warp] = n;
-        }
+    // ---- triangles: one thread per surface cube (row by binary search over the per-row cube counts) ----
+    if (do_tris) {
+        __shared__ int s_sp[256];
+        s_sp[tid] = __popc((unsigned)s_r16[R16_SURF + tid]);
         __syncthreads();
-        if (warp == 0) warp0_exclusive_scan(s_tsum, 128, lane);
+        int ncubes = 0;
+        if (tid < 32) ncubes = warp0_exclusive_scan(s_sp, 256, tid);
+        __shared__ int s_ncubes;
+        if (tid == 0) s_ncubes = ncubes;
         __syncthreads();
-        for (int it = 0; it < 16; ++it) {
-            int c = cube[it];
-            int n = s_tric[c];
-            int incl = n;
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
+        ncubes = s_ncubes;
+        for (int j = tid; j < ncubes; j += 256) {
+            int lo = 0, hi = 255;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_sp[mid] <= j) lo = mid; else hi = mid - 1;
             }
-            if (n == 0) continue;
-            int64_t tbase = toff + s_tsum[it * 8 + warp] + incl - n;
-            int v = it * 256 + tid;
-            int x = v & 15, y = (v >> 4) & 15, z = v >> 8;
-            for (int k = 0; k < n; ++k) {
+            const int row = lo, y = row & 15, z = row >> 4;
+            const unsigned surf = s_r16[R16_SURF + row];
+            const int kth = j - s_sp[row];
+            const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
+            const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
+            int64_t tbase = toff + s_r16[R16_TPREF + row];
+            unsigned before = surf;
+            int x = 0;
+            for (int q = 0; q <= kth; ++q, before &= before - 1) {     // triangles of the earlier cubes of the row
+                x = __ffs(before) - 1;
+                if (q < kth) tbase += MC_TRI_COUNT[cube_case(s00, s10, s01, s11, x + 1)];
+            }
+            {
+                const int c = cube_case(s00, s10, s01, s11, x + 1);
+                for (int k = 0; k < 15 && s_tt[c * 16 + k] >= 0; k += 3, ++tbase) {
 #pragma unroll
-                for (int vtx = 0; vtx < 3; ++vtx) {
-                    int edge = s_tt[c * 16 + 3 * k + vtx];
-                    int ox = x + MC_EDGE_SHIFTS[edge][0], oy = y + MC_EDGE_SHIFTS[edge][1], oz = z + MC_EDGE_SHIFTS[edge][2];
-                    int ax = MC_EDGE_SHIFTS[edge][3];
-                    int nbk = nb_of(ox) + 3 * nb_of(oy) + 9 * nb_of(oz);
-                    int lv = ((oz & 15) * 16 + (oy & 15)) * 16 + (ox & 15);
-                    int w = ax * 128 + (lv >> 5);
-                    unsigned low = (1u << (lv & 31)) - 1u;
-                    int64_t id;
-                    if (nbk == 13) {
-                        id = voff + s_pref[w] + __popc(s_mask[w] & low);
-                    } else {
-                        int64_t bn = s_nb[nbk];
-                        id = offsets[2 * bn] + eprefix[bn * EWORDS + w] + __popc(emask[bn * EWORDS + w] & low);
+                    for (int vtx = 0; vtx < 3; ++vtx) {
+                        const int edge = s_tt[c * 16 + k + vtx];
+                        const int ox = x + MC_EDGE_SHIFTS[edge][0], oy = y + MC_EDGE_SHIFTS[edge][1],
+                                  oz = z + MC_EDGE_SHIFTS[edge][2], ax = MC_EDGE_SHIFTS[edge][3];
+                        const int nbk = nb_of(ox) + 3 * nb_of(oy) + 9 * nb_of(oz);
+                        const int item = ax * 256 + (oz & 15) * 16 + (oy & 15);
+                        const unsigned low = (1u << (ox & 15)) - 1u;
+                        int64_t id;
+                        if (nbk == 13) {
+                            id = voff + s_r16[R16_EPREF + item] + __popc(s_r16[R16_EMASK + item] & low);
+                        } else {
+                            const int64_t bn = s_nb[nbk];
+                            const uint16_t *rn = rows16 + bn * R16_WORDS;
+                            id = offsets[2 * bn] + __ldg(rn + R16_EPREF + item) + __popc(__ldg(rn + R16_EMASK + item) & low);
+                        }
+                        tris[3 * tbase + (2 - vtx)] = (int32_t)id;   // winding reversed
                     }
-                    tris[3 * (tbase + k) + (2 - vtx)] = (int32_t)id;   // winding reversed
                 }
             }
         }
@@ -351,8 +435,27 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
 }
 
 // ------------------------------------------------------------------------------------------------
-// point cloud: count + emit (weights read directly; tsdf neighbourhood staged for normals)
+// point cloud: count + emit.  The crossing test is Open3D's `tsdf_i * tsdf_o < 0` on the float product
+// (not a sign comparison: a zero or an underflowing product does not count), so it stays per voxel.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tsdf(const float *__restrict__ tsdf, const int *s_nb, float *s_t, int tid) {
+    for (int r = tid; r < TS_R * TS_R * TS_R; r += 256) {
+        int rx = r % TS_R - 1, ry = (r / TS_R) % TS_R - 1, rz = r / (TS_R * TS_R) - 1;
+        int bi = s_nb[nb_of(rx) + 3 * nb_of(ry) + 9 * nb_of(rz)];
+        float t = 0.0f;
+        if (bi >= 0) t = __ldg(tsdf + (int64_t)bi * MQ3D_RES3 + (((rz & 15) * 16 + (ry & 15)) * 16 + (rx & 15)));
+        s_t[r] = t;
+    }
+}
+#define TS(ix, iy, iz) s_t[(((iz) + 1) * TS_R + (iy) + 1) * TS_R + (ix) + 1]
+#define EXISTS(ix, iy, iz) (s_nb[nb_of(ix) + 3 * nb_of(iy) + 9 * nb_of(iz)] >= 0)
+
+__device__ __forceinline__ void get_normal(const float *s_t, const int *s_nb, int x, int y, int z, float *n) {
+    if (EXISTS(x + 1, y, z) && EXISTS(x - 1, y, z)) n[0] = __fsub_rn(TS(x + 1, y, z), TS(x - 1, y, z));
+    if (EXISTS(x, y + 1, z) && EXISTS(x, y - 1, z)) n[1] = __fsub_rn(TS(x, y + 1, z), TS(x, y - 1, z));
+    if (EXISTS(x, y, z + 1) && EXISTS(x, y, z - 1)) n[2] = __fsub_rn(TS(x, y, z + 1), TS(x, y, z - 1));
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(256)
 k_points(const float *__restrict__ tsdf, const float *__restrict__ weight, const int32_t *__restrict__ block_keys,
@@ -439,16 +542,13 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
     int64_t n = g->n_blocks_host;
     MQ3D_REQUIRE(n <= g->capacity, "internal: block count exceeds pool capacity");
     if (n > g->mc_alloc_blocks || g->mc_offsets == nullptr) {
-        cudaFree(g->mc_nb); cudaFree(g->mc_emask); cudaFree(g->mc_eprefix); cudaFree(g->mc_cubes);
-        cudaFree(g->mc_counts); cudaFree(g->mc_offsets);
-        g->mc_nb = nullptr; g->mc_emask = nullptr; g->mc_eprefix = nullptr; g->mc_cubes = nullptr;
-        g->mc_counts = nullptr; g->mc_offsets = nullptr;
+        cudaFree(g->mc_nb); cudaFree(g->mc_emask); cudaFree(g->mc_eprefix); cudaFree(g->mc_counts); cudaFree(g->mc_offsets);
+        g->mc_nb = nullptr; g->mc_emask = nullptr; g->mc_eprefix = nullptr; g->mc_counts = nullptr; g->mc_offsets = nullptr;
         g->mc_alloc_blocks = 0;
         int64_t a = n + n / 4 + 16;
         MQ3D_CUDA(cudaMalloc(&g->mc_nb, sizeof(int32_t) * 27 * a));
-        MQ3D_CUDA(cudaMalloc(&g->mc_emask, sizeof(uint32_t) * EWORDS * a));
-        MQ3D_CUDA(cudaMalloc(&g->mc_eprefix, sizeof(uint16_t) * EWORDS * a));
-        MQ3D_CUDA(cudaMalloc(&g->mc_cubes, sizeof(uint8_t) * MQ3D_RES3 * a));
+        MQ3D_CUDA(cudaMalloc(&g->mc_emask, sizeof(uint32_t) * SROW_WORDS * a));     // sign rows
+        MQ3D_CUDA(cudaMalloc(&g->mc_eprefix, sizeof(uint16_t) * R16_WORDS * a));    // 16-bit row tables
         MQ3D_CUDA(cudaMalloc(&g->mc_counts, sizeof(int32_t) * 2 * a));
         MQ3D_CUDA(cudaMalloc(&g->mc_offsets, sizeof(int64_t) * 2 * (a + 1)));
         g->mc_alloc_blocks = a;
@@ -465,11 +565,10 @@ static int mc_finish_count(mq3d_grid *g, cudaStream_t st, int64_t *a, int64_t *b
     int64_t n = g->mc_blocks;
     k_scan_counts<<<1, 1024, 0, st>>>(g->mc_counts, n, g->mc_offsets);
     MQ3D_CUDA(cudaGetLastError());
-    int64_t tot[2];
-    MQ3D_CUDA(cudaMemcpyAsync(tot, g->mc_offsets + 2 * n, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host64, g->mc_offsets + 2 * n, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
     MQ3D_CUDA(cudaStreamSynchronize(st));
-    *a = tot[0];
-    *b = tot[1];
+    *a = g->pinned_host64[0];
+    *b = g->pinned_host64[1];
     return MQ3D_OK;
 }
 
@@ -483,7 +582,7 @@ extern "C" int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int
     int64_t n = g->mc_blocks;
     if (n > 0) {
         k_mc_classify<<<(unsigned)n, 256, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, weight_threshold, g->part,
-                                                   g->mc_emask, g->mc_eprefix, g->mc_cubes, g->mc_counts);
+                                                   g->mc_emask, g->mc_eprefix, g->mc_counts);
         MQ3D_CUDA(cudaGetLastError());
     }
     MQ3D_TRY(mc_finish_count(g, st, &g->mc_V, &g->mc_T));
@@ -507,8 +606,8 @@ extern "C" int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *
     cudaStream_t st = as_stream(stream);
     if (g->mc_blocks > 0 && (g->mc_V > 0 || g->mc_T > 0)) {
         k_mc_emit<<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->block_keys, g->mc_nb, g->mc_emask, g->mc_eprefix,
-                                                          g->mc_cubes, g->mc_counts, g->mc_offsets, g->voxel_size,
-                                                          vertices_dev, normals_dev, triangles_dev, vertex_keys_dev);
+                                                          g->mc_counts, g->mc_offsets, g->voxel_size, vertices_dev,
+                                                          normals_dev, triangles_dev, vertex_keys_dev);
         MQ3D_CUDA(cudaGetLastError());
     }
     return MQ3D_OK;

@@ -44,17 +44,62 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     conf/count (float64 / int32 [F,H,W], host or device) enable the reference's confidence mask
     (o3d_utils.py:131-142).  colors_host: uint8 [F,CH,CW,3] enables Open3D's colour overload."""
     dev = vbg.device
-    raw = raw_host.to(dev, non_blocking=True)
+    F = int(raw_host.shape[0])
     mask = params.use_confidence_filtered_depth and conf is not None
-    lin, valid = depth_prepare(raw, nears, fars,
-                               conf.to(dev, non_blocking=True) if mask else None,
-                               count.to(dev, non_blocking=True) if mask else None,
-                               has_conf if mask else None,
-                               params.confidence_threshold, params.valid_count_threshold)
-    colors = colors_host.to(dev, non_blocking=True) if colors_host is not None and vbg.has_color else None
-    return vbg.integrate_sequence(lin, K, E_wc, params.depth_max, params.trunc_voxel_multiplier, 1.0,
-                                  frame_valid=valid, colors=colors, color_intrinsics=Kc,
-                                  batch_frames=params.batch_frames)
+    use_color = colors_host is not None and vbg.has_color
+    chunk = max(1, int(params.batch_frames))
+    K = np.asarray(K)
+    E_wc = np.asarray(E_wc)
+    nears = np.asarray(nears, dtype=np.float64)
+    fars = np.asarray(fars, dtype=np.float64)
+    # Chunked pipeline: a copy stream uploads chunk k+1 (pinned host -> HBM) while the compute stream
+    # runs K1 + fused K2/K3 on chunk k; one event per chunk orders the two streams.
+    main = torch.cuda.current_stream(dev)
+    copy = _copy_stream(dev)
+    copy.wait_stream(main)
+    staged = []
+    for f0 in range(0, F, chunk):
+        f1 = min(F, f0 + chunk)
+        with torch.cuda.stream(copy):
+            part = {"raw": raw_host[f0:f1].to(dev, non_blocking=True)}
+            if use_color:
+                part["col"] = colors_host[f0:f1].to(dev, non_blocking=True)
+            if mask:
+                part["conf"] = conf[f0:f1].to(dev, non_blocking=True)
+                part["count"] = count[f0:f1].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        staged.append((f0, f1, part, ev))
+    total = None
+    for f0, f1, part, ev in staged:
+        main.wait_event(ev)
+        for t in part.values():
+            t.record_stream(main)
+        lin, valid = depth_prepare(part["raw"], nears[f0:f1], fars[f0:f1], part.get("conf"), part.get("count"),
+                                   None if (has_conf is None or not mask) else has_conf[f0:f1],
+                                   params.confidence_threshold, params.valid_count_threshold)
+        st = vbg.integrate_sequence(lin, K[f0:f1], E_wc[f0:f1], params.depth_max, params.trunc_voxel_multiplier, 1.0,
+                                    frame_valid=valid, colors=part.get("col"),
+                                    color_intrinsics=None if Kc is None else np.asarray(Kc)[f0:f1],
+                                    batch_frames=chunk)
+        if total is None:
+            total = st
+        else:
+            total = SequenceStats(total.frames_integrated + st.frames_integrated, total.block_visits + st.block_visits,
+                                  total.blocks_loaded + st.blocks_loaded, st.num_blocks, total.batches + st.batches,
+                                  total.voxel_updates + st.voxel_updates, total.touch_ms + st.touch_ms,
+                                  total.integrate_ms + st.integrate_ms)
+    return total
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.type, dev.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
 
 
 def extract_mesh_to_host(vbg: VoxelBlockGrid, weight_threshold: float):

@@ -131,3 +131,40 @@ def test_compat_layer_runs_the_reference_frame_loop(cuda_device, oracle):
     assert depth.shape == (80, 80)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         o3d.t.geometry.VoxelBlockGrid(voxel_size=0.02, block_count=10, device=o3d.core.Device("CPU:0"))
+
+
+def test_integrate_frames_host_pipeline_matches_direct(cuda_device, oracle):
+    """The chunked H2D/compute pipeline (public host-buffer API used by bench.py's e2e number) gives the
+    same grid as one fused call on device-resident frames."""
+    import mq3d_b200  # noqa: F401
+    from helpers import capture
+    from mq3d_b200 import synth
+    from mq3d_b200.pipeline import IntegrationParams, extract_mesh_to_host, integrate_frames, pin
+    from mq3d_b200.vbg import VoxelBlockGrid, depth_prepare
+    n = 11
+    cap = capture(n)
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    colors = np.stack([synth.make_color_frame(Ecw[i], width=160, height=120, f=110.0) for i in range(n)])
+    Kc = np.tile(np.array([[110.0, 0, 80.0], [0, 110.0, 60.0], [0, 0, 1.0]]), (n, 1, 1))
+    rng = np.random.default_rng(3)
+    conf = rng.random(cap.raw.shape)
+    count = rng.integers(0, 6, cap.raw.shape).astype(np.int32)
+    names = ("tsdf", "weight", "color")
+    a = VoxelBlockGrid(attr_names=names, voxel_size=0.02, block_count=300, device=cuda_device)
+    p = IntegrationParams(voxel_size=0.02, depth_max=4.0, trunc_voxel_multiplier=10.0, confidence_threshold=0.3,
+                          valid_count_threshold=2, batch_frames=4)
+    st = integrate_frames(a, pin(cap.raw), ds.nears, ds.fars, K, Ewc, p, conf=pin(conf), count=pin(count),
+                          colors_host=pin(colors), Kc=Kc)
+    b = VoxelBlockGrid(attr_names=names, voxel_size=0.02, block_count=300, device=cuda_device)
+    lin, valid = depth_prepare(torch.from_numpy(cap.raw).to(cuda_device), ds.nears, ds.fars,
+                               torch.from_numpy(conf).to(cuda_device), torch.from_numpy(count).to(cuda_device), None, 0.3, 2)
+    st2 = b.integrate_sequence(lin, K, Ewc, 4.0, 10.0, frame_valid=valid, colors=torch.from_numpy(colors).to(cuda_device),
+                               color_intrinsics=Kc, batch_frames=64)
+    assert (st.frames_integrated, st.block_visits, st.voxel_updates, st.num_blocks, st.batches) == \
+        (st2.frames_integrated, st2.block_visits, st2.voxel_updates, st2.num_blocks, 3)
+    for x, y in zip(sort_blocks(*[t.cpu().numpy() for t in a.export_blocks()]),
+                    sort_blocks(*[t.cpu().numpy() for t in b.export_blocks()])):
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x, y.view(np.uint32) if y.dtype == np.float32 else y)
+    v, nrm, t = extract_mesh_to_host(a, 1.5)
+    assert v.dtype == np.float32 and t.dtype == np.int32 and len(t) > 100
