@@ -167,7 +167,7 @@ def run_gpu(args):
     vbg = VoxelBlockGrid(attr_names=("tsdf", "weight", "color") if color else ("tsdf", "weight"),
                          voxel_size=cfg["voxel"], block_count=cfg["block_count"], device=device)
     if world > 1:
-        vbg.set_partition(rank, world, args.tile)
+        vbg.set_partition(rank, world, args.tile, integrate_ghosts=(args.ghosts == "integrate"))
     params = IntegrationParams(voxel_size=cfg["voxel"], block_count=cfg["block_count"], depth_max=cfg["depth_max"],
                                trunc_voxel_multiplier=cfg["trunc"], use_confidence_filtered_depth=False,
                                batch_frames=args.batch)
@@ -183,14 +183,26 @@ def run_gpu(args):
         lin, valid = depth_prepare(wl["raw"], wl["nears"], wl["fars"])
         st = vbg.integrate_sequence(lin, wl["K"], wl["Ewc"], cfg["depth_max"], cfg["trunc"], 1.0, frame_valid=valid,
                                     colors=wl["colors"], color_intrinsics=wl["Kc"], batch_frames=args.batch)
+        t_a = time.perf_counter()
+        if world > 1 and args.ghosts == "exchange":
+            from mq3d_b200.dist import exchange_ghosts
+            exchange_ghosts(vbg, rank, world)        # owners -> ghost shells, once, before extraction
+            torch.cuda.synchronize()
+        t_b = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
         e1.record()
+        t_c = time.perf_counter()
         if world > 1:            # the north star's "final gather": per-rank meshes -> rank 0 over NCCL
             from mq3d_b200.dist import gather_mesh
             gather_mesh(v, nrm, t, dst=0)
+            torch.cuda.synchronize()
+        mgpu_ms["exchange"].append((t_b - t_a) * 1e3)
+        mgpu_ms["gather"].append((time.perf_counter() - t_c) * 1e3)
         return st, (v, nrm, t), (e0, e1)
+
+    mgpu_ms = {"exchange": [], "gather": []}
 
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -228,6 +240,9 @@ def run_gpu(args):
         vbg.reset()
         integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params, colors_host=col_host,
                          Kc=wl["Kc"])
+        if world > 1 and args.ghosts == "exchange":
+            from mq3d_b200.dist import exchange_ghosts
+            exchange_ghosts(vbg, rank, world)
         return extract_mesh_to_host(vbg, cfg["weight_thr"])
 
     for _ in range(min(args.warmup, 2)):
@@ -282,13 +297,14 @@ def run_gpu(args):
                    "color": "1280x960 u8 RGB" if color else None, "voxel_size": cfg["voxel"], "block": "16^3",
                    "trunc_voxel_multiplier": cfg["trunc"], "depth_max": cfg["depth_max"],
                    "weight_threshold": cfg["weight_thr"], "batch_frames": args.batch,
-                   "partition": f"tile-hash T={args.tile}, ghost shell" if world > 1 else "single GPU",
+                   "partition": f"tile-hash T={args.tile}, ghost shell by {args.ghosts}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (depth+RGB sequence > 126 MB); no explicit flush"},
         "gvoxel_updates_per_s": visits / (ms_per_step * 1e-3) / 1e9,
         "gvoxel_visits_per_s_integrate_kernel": visits / (integ_ms * 1e-3) / 1e9,
         "updated_voxel_fraction": updates / max(visits, 1),
         "mc_ms": mc_ms, "mesh": {"vertices": V, "triangles": T}, "active_blocks": nblocks,
         "kernel_ms": {"k_integrate": integ_ms, "k_touch": touch_ms, "mc_count+fill": mc_ms},
+        "multi_gpu_ms_rank0": {k: float(np.median(v[-args.steps:])) for k, v in mgpu_ms.items()} if world > 1 else None,
         "roofline": {"bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "bytes_per_voxel_visit": bytes_per_visit,
@@ -400,7 +416,10 @@ def main():
     ap.add_argument("--workload", default="quest300_rgb_v10mm", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames per side")
     ap.add_argument("--batch", type=int, default=64, help="frames per block residency (<= 256)")
-    ap.add_argument("--tile", type=int, default=8, help="partition super-tile edge in blocks (N > 1)")
+    ap.add_argument("--tile", type=int, default=4, help="partition super-tile edge in blocks (N > 1)")
+    ap.add_argument("--ghosts", default="exchange", choices=["exchange", "integrate"],
+                    help="N > 1: 'integrate' = every rank also integrates its ghost shell (no exchange, the "
+                         "north-star scheme); 'exchange' = owned blocks only + one ghost-block exchange before MC")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -76,6 +76,16 @@ int mq3d_grid_import(mq3d_grid *g, const int32_t *keys_dev, const float *tsdf_de
  * (tile_blocks^3 blocks) hashes to `rank` of `world`, plus the one-block ghost shell around them.
  * world == 1 disables filtering.  Must be called on an empty grid. */
 int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int tile_blocks);
+/* integrate_ghosts = 1 (default): frames are integrated into owned + ghost blocks, no exchange is ever
+ * needed (the north-star scheme).  integrate_ghosts = 0: only owned blocks are integrated (no redundant
+ * work) and the ghost shell is fetched once from the owners before extraction: the owner calls
+ * mq3d_grid_ghost_select(dest) (first with keys_dev == NULL for the count, then with buffers:
+ * keys int32 [n][3], tsdf/weight float32 [n][4096], color float32 [n][4096][3] or NULL), the host moves
+ * the payload (NCCL send/recv) and the receiver calls mq3d_grid_import.  Values are the owner's, i.e.
+ * bit-identical to what redundant integration would have produced. */
+int mq3d_grid_set_ghost_mode(mq3d_grid *g, int integrate_ghosts);
+int mq3d_grid_ghost_select(mq3d_grid *g, int dest_rank, int64_t *n_out, int32_t *keys_dev, float *tsdf_dev,
+                           float *weight_dev, float *color_dev, void *stream);
 
 /* ---- K1: raw NDC depth -> linear metres + confidence mask -----------------------------------
  * Replaces DepthDataIO.load_depth_map's convert_depth_to_linear + is_depth_map_valid

@@ -112,6 +112,8 @@ __device__ __forceinline__ uint32_t hash_find(const HashView &h, uint64_t key) {
 // ------------------------------------------------------------------------------------------------
 struct Partition {
     int rank, world, tile_shift;  // tile = 1 << tile_shift blocks per axis
+    int integrate_ghosts;         // 1: frames are integrated into owned + ghost blocks (no exchange);
+                                  // 0: owned blocks only, ghosts are fetched from their owners before extraction
 };
 
 __host__ __device__ __forceinline__ int mq3d_tile_owner(int bx, int by, int bz, const Partition &p) {
@@ -121,6 +123,9 @@ __host__ __device__ __forceinline__ int mq3d_tile_owner(int bx, int by, int bz, 
 __host__ __device__ __forceinline__ bool mq3d_block_owned(int bx, int by, int bz, const Partition &p) {
     return p.world <= 1 || mq3d_tile_owner(bx, by, bz, p) == p.rank;
 }
+// blocks a frame is integrated into on this rank
+#define MQ3D_INTEGRATES(bx, by, bz, p) \
+    ((p).integrate_ghosts ? mq3d_block_needed(bx, by, bz, p) : mq3d_block_owned(bx, by, bz, p))
 // block is kept on this rank if it or any of its 26 neighbours lies in an owned tile
 __host__ __device__ __forceinline__ bool mq3d_block_needed(int bx, int by, int bz, const Partition &p) {
     if (p.world <= 1) return true;
@@ -236,4 +241,4 @@ int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st);                 // refr
 int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool *rehashed);
 int mq3d_set_device(int device);
 // Activate + Find for an explicit key list; block indices land in g->idx_scratch.
-int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, cudaStream_t st);
+int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st);

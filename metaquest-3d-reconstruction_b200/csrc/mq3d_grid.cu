@@ -118,6 +118,7 @@ extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t 
     g->part.rank = 0;
     g->part.world = 1;
     g->part.tile_shift = 3;
+    g->part.integrate_ghosts = 1;
     g->capacity = block_count;
     g->table_size = next_pow2(block_count * 2 < 1024 ? 1024 : block_count * 2);
     cudaStream_t st = 0;
@@ -226,6 +227,83 @@ extern "C" int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int ti
     g->part.rank = rank;
     g->part.world = world;
     g->part.tile_shift = shift;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_set_ghost_mode(mq3d_grid *g, int integrate_ghosts) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    MQ3D_REQUIRE(g->n_blocks_host == 0, "ghost mode must be set on an empty grid");
+    g->part.integrate_ghosts = integrate_ghosts ? 1 : 0;
+    return MQ3D_OK;
+}
+
+// flag the owned blocks that `dest` keeps as ghosts and compact their indices (order arbitrary)
+__global__ void k_ghost_select(const int32_t *__restrict__ block_keys, int64_t n, Partition part, int dest,
+                               int *__restrict__ count, int32_t *__restrict__ idx_out) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    int x = block_keys[3 * b], y = block_keys[3 * b + 1], z = block_keys[3 * b + 2];
+    if (!mq3d_block_owned(x, y, z, part)) return;
+    Partition pd = part;
+    pd.rank = dest;
+    if (!mq3d_block_needed(x, y, z, pd)) return;
+    int i = atomicAdd(count, 1);
+    if (idx_out) idx_out[i] = (int32_t)b;
+}
+
+__global__ void k_ghost_gather(const int32_t *__restrict__ idx, const int32_t *__restrict__ block_keys,
+                               const float *__restrict__ tsdf, const float *__restrict__ weight,
+                               const float *__restrict__ color, int32_t *__restrict__ keys_out, float *__restrict__ tsdf_out,
+                               float *__restrict__ weight_out, float *__restrict__ color_out) {
+    const int64_t i = blockIdx.x;
+    const int64_t b = idx[i];
+    if (threadIdx.x < 3) keys_out[3 * i + threadIdx.x] = block_keys[3 * b + threadIdx.x];
+    const float4 *st = reinterpret_cast<const float4 *>(tsdf + b * MQ3D_RES3);
+    const float4 *sw = reinterpret_cast<const float4 *>(weight + b * MQ3D_RES3);
+    float4 *dt = reinterpret_cast<float4 *>(tsdf_out + i * MQ3D_RES3);
+    float4 *dw = reinterpret_cast<float4 *>(weight_out + i * MQ3D_RES3);
+    for (int k = threadIdx.x; k < MQ3D_RES3 / 4; k += blockDim.x) {
+        dt[k] = st[k];
+        dw[k] = sw[k];
+    }
+    if (color && color_out) {
+        const float4 *sc = reinterpret_cast<const float4 *>(color + b * 3 * MQ3D_RES3);
+        float4 *dc = reinterpret_cast<float4 *>(color_out + i * 3 * MQ3D_RES3);
+        for (int k = threadIdx.x; k < 3 * MQ3D_RES3 / 4; k += blockDim.x) dc[k] = sc[k];
+    }
+}
+
+extern "C" int mq3d_grid_ghost_select(mq3d_grid *g, int dest_rank, int64_t *n_out, int32_t *keys_dev, float *tsdf_dev,
+                                      float *weight_dev, float *color_dev, void *stream) {
+    MQ3D_REQUIRE(g && n_out, "null argument");
+    MQ3D_REQUIRE(dest_rank >= 0 && dest_rank < g->part.world, "bad destination rank");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    const int64_t n = g->n_blocks_host;
+    *n_out = 0;
+    if (n == 0 || dest_rank == g->part.rank) return MQ3D_OK;
+    if (n > g->idx_scratch_size) {
+        cudaFree(g->idx_scratch);
+        g->idx_scratch = nullptr;
+        g->idx_scratch_size = 0;
+        MQ3D_CUDA(cudaMalloc(&g->idx_scratch, sizeof(int32_t) * next_pow2(n)));
+        g->idx_scratch_size = next_pow2(n);
+    }
+    MQ3D_CUDA(cudaMemsetAsync(g->counter_dev + 5, 0, sizeof(int), st));
+    k_ghost_select<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->block_keys, n, g->part, dest_rank, g->counter_dev + 5,
+                                                                keys_dev ? g->idx_scratch : nullptr);
+    MQ3D_CUDA(cudaGetLastError());
+    MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host + 5, g->counter_dev + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MQ3D_CUDA(cudaStreamSynchronize(st));
+    const int64_t m = g->pinned_host[5];
+    *n_out = m;
+    if (keys_dev && m > 0) {
+        MQ3D_REQUIRE(tsdf_dev && weight_dev, "null ghost payload buffers");
+        k_ghost_gather<<<(unsigned)m, 256, 0, st>>>(g->idx_scratch, g->block_keys, g->tsdf, g->weight, g->color, keys_dev,
+                                                    tsdf_dev, weight_dev, color_dev);
+        MQ3D_CUDA(cudaGetLastError());
+    }
     return MQ3D_OK;
 }
 
@@ -354,8 +432,10 @@ extern "C" int mq3d_grid_export(mq3d_grid *g, int32_t *keys_dev, float *tsdf_dev
 // ------------------------------------------------------------------------------------------------
 // activation of explicit key lists (per-frame integrate, import)
 // ------------------------------------------------------------------------------------------------
+// integrating = true : keys of a frame about to be integrated -> blocks this rank integrates
+// integrating = false: import (VoxelBlockGrid.load, ghost exchange)  -> any block this rank keeps
 __global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int *n_blocks, int32_t *block_keys,
-                                int64_t capacity, Partition part, int *bad_key_flag) {
+                                int64_t capacity, Partition part, bool integrating, int *bad_key_flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
@@ -363,7 +443,7 @@ __global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int 
         *bad_key_flag = 1;
         return;
     }
-    if (!mq3d_block_needed(x, y, z, part)) return;
+    if (integrating ? !MQ3D_INTEGRATES(x, y, z, part) : !mq3d_block_needed(x, y, z, part)) return;
     bool fresh;
     uint32_t s = hash_insert(h, mq3d_pack_key(x, y, z), fresh);
     if (fresh) {
@@ -377,12 +457,13 @@ __global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int 
     }
 }
 
-__global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, int32_t *idx_out) {
+__global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, Partition part, bool integrating,
+                            int32_t *idx_out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
     int32_t r = -1;
-    if (mq3d_key_in_range(x, y, z)) {
+    if (mq3d_key_in_range(x, y, z) && (!integrating || MQ3D_INTEGRATES(x, y, z, part))) {
         uint32_t s = hash_find(h, mq3d_pack_key(x, y, z));
         if (s != 0xFFFFFFFFu) r = h.vals[s];
     }
@@ -390,7 +471,7 @@ __global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, int32_t 
 }
 
 // Activate + Find (Open3D Integrate preamble).  Leaves block indices in g->idx_scratch.
-int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, cudaStream_t st) {
+int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st) {
     if (n > g->idx_scratch_size) {
         cudaFree(g->idx_scratch);
         g->idx_scratch = nullptr;
@@ -405,8 +486,8 @@ int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, cudaStr
     MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int), st));
     unsigned grid = (unsigned)((n + 255) / 256);
     k_activate_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->n_blocks_dev, g->block_keys, g->capacity,
-                                          g->part, g->counter_dev);
-    k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->idx_scratch);
+                                          g->part, integrating, g->counter_dev);
+    k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->part, integrating, g->idx_scratch);
     MQ3D_CUDA(cudaGetLastError());
     g->mc_state = 0;
     return MQ3D_OK;
@@ -441,7 +522,7 @@ extern "C" int mq3d_grid_import(mq3d_grid *g, const int32_t *keys_dev, const flo
     MQ3D_REQUIRE(keys_dev && tsdf_dev && weight_dev, "null block arrays");
     MQ3D_TRY(mq3d_set_device(g->device));
     cudaStream_t st = as_stream(stream);
-    MQ3D_TRY(mq3d_grid_activate(g, keys_dev, n, st));
+    MQ3D_TRY(mq3d_grid_activate(g, keys_dev, n, /*integrating=*/false, st));
     k_import_values<<<(unsigned)n, 256, 0, st>>>(g->idx_scratch, n, tsdf_dev, weight_dev, color_dev, g->tsdf,
                                                   g->weight, g->color);
     MQ3D_CUDA(cudaGetLastError());

@@ -58,6 +58,71 @@ def broadcast_frames(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     return t
 
 
+def _pack_ghosts(vbg, dest: int):
+    """(flat float32 payload, block count, has_color) for `dest`; layout = vbg.ghost_packed_len/ghost_views."""
+    from .vbg import ghost_packed_len, ghost_views
+    if hasattr(vbg, "ghost_select_packed"):
+        return vbg.ghost_select_packed(dest)
+    k, t, w, c = vbg.ghost_select(dest)
+    m, has_color = int(k.shape[0]), c is not None
+    buf = torch.zeros(ghost_packed_len(m, has_color), dtype=torch.float32, device=k.device)
+    if m:
+        for dst, src in zip(ghost_views(buf, m, has_color), (k, t, w, c)):
+            if dst is not None:
+                dst.copy_(src.reshape(dst.shape))
+    return buf, m, has_color
+
+
+def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None) -> int:
+    """Owned-only integration mode: fetch the ghost shell from the owners.  One all-gather of the
+    [world x world] block-count matrix, then one packed send/recv per rank pair (keys | tsdf | weight |
+    colour in a single buffer), then one import.  `vbg` needs ghost_select(dest) (or ghost_select_packed)
+    and import_blocks(keys, tsdf, weight, color).  Returns the number of ghost blocks received.  The payload
+    is the owners' block values, so afterwards the local grid is bit-identical to one that integrated its
+    ghosts redundantly."""
+    import torch.distributed as dist
+    from .vbg import ghost_packed_len, ghost_views
+    if rank is None:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return 0
+    outgoing = {d: _pack_ghosts(vbg, d) for d in range(world) if d != rank}
+    first = next(iter(outgoing.values()))
+    dev, has_color = first[0].device, first[2]
+    send_n = torch.zeros(world, dtype=torch.int64, device=dev)
+    for d, (_, m, _) in outgoing.items():
+        send_n[d] = m
+    matrix = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(matrix, send_n)                       # matrix[src][dst] = blocks src sends to dst
+    recv_n = [int(matrix[p][rank]) for p in range(world)]
+    total = sum(recv_n[p] for p in range(world) if p != rank)
+    # all incoming payloads land in slices of ONE buffer laid out as a single packed payload of `total`
+    # blocks would need a gather; instead keep per-peer packed buffers and import them together
+    incoming, ops = {}, []
+    for p in range(world):
+        if p == rank:
+            continue
+        buf, m, _ = outgoing[p]
+        if m:
+            ops.append(dist.P2POp(dist.isend, buf, p))
+        if recv_n[p]:
+            incoming[p] = torch.empty(ghost_packed_len(recv_n[p], has_color), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, incoming[p], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if not incoming:
+        return 0
+    parts = [ghost_views(buf, recv_n[p], has_color) for p, buf in incoming.items()]
+    if len(parts) == 1:
+        k, t, w, c = parts[0]
+    else:
+        k, t, w = (torch.cat([x[i] for x in parts]) for i in range(3))
+        c = torch.cat([x[3] for x in parts]) if has_color else None
+    vbg.import_blocks(k, t, w, c)
+    return total
+
+
 def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangles: torch.Tensor, dst: int = 0):
     """Concatenate per-rank meshes on `dst`: vertex arrays are appended in rank order and triangle
     indices rebased by the exclusive scan of the per-rank vertex counts.  Returns (vertices, normals,

@@ -64,6 +64,23 @@ def as_depth_tensor(depth, device: torch.device) -> torch.Tensor:
     return depth.to(device, non_blocking=True).contiguous()
 
 
+def ghost_packed_len(m: int, has_color: bool) -> int:
+    """float32 words of one packed ghost payload: keys (padded to 16 B) | tsdf | weight | colour."""
+    return ((3 * m + 3) // 4) * 4 + m * RES ** 3 * (5 if has_color else 2)
+
+
+def ghost_views(buf: torch.Tensor, m: int, has_color: bool):
+    """(keys i32 [m,3], tsdf [m,4096], weight [m,4096], color [m,4096,3] | None) views of a packed payload;
+    `keys.untyped_storage()` is the single contiguous buffer that travels between ranks."""
+    v = RES ** 3
+    k_len = ((3 * m + 3) // 4) * 4
+    keys = buf[: 3 * m].view(torch.int32).view(m, 3)
+    tsdf = buf[k_len: k_len + m * v].view(m, v)
+    weight = buf[k_len + m * v: k_len + 2 * m * v].view(m, v)
+    color = buf[k_len + 2 * m * v: k_len + 5 * m * v].view(m, v, 3) if has_color else None
+    return keys, tsdf, weight, color
+
+
 @dataclass
 class SequenceStats:
     frames_integrated: int
@@ -144,8 +161,36 @@ class VoxelBlockGrid:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mq3d_grid_reset(self._h, _stream()))
 
-    def set_partition(self, rank: int, world: int, tile_blocks: int = 8):
+    def set_partition(self, rank: int, world: int, tile_blocks: int = 8, integrate_ghosts: bool = True):
+        """Hash partition for multi-GPU runs.  integrate_ghosts=False integrates owned blocks only; call
+        dist.exchange_ghosts(vbg) before extracting."""
         _lib.check(_lib.lib().mq3d_grid_set_partition(self._h, int(rank), int(world), int(tile_blocks)))
+        _lib.check(_lib.lib().mq3d_grid_set_ghost_mode(self._h, int(bool(integrate_ghosts))))
+        self.partition = (int(rank), int(world), int(tile_blocks), bool(integrate_ghosts))
+
+    def ghost_select(self, dest_rank: int):
+        """Owned blocks that `dest_rank` keeps as ghosts: (keys i32 [n,3], tsdf f32 [n,4096], weight f32
+        [n,4096], color f32 [n,4096,3] | None) device tensors."""
+        buf, m, has_color = self.ghost_select_packed(dest_rank)
+        return ghost_views(buf, m, has_color)
+
+    def ghost_select_packed(self, dest_rank: int):
+        """Same selection as one contiguous float32 payload (see ghost_packed_len / ghost_views):
+        (buffer, block count, has_color)."""
+        n = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_ghost_select(self._h, int(dest_rank), C.byref(n), None, None, None, None,
+                                                         _stream()))
+            m = int(n.value)
+            buf = torch.empty(ghost_packed_len(m, self.has_color), dtype=torch.float32, device=self.device)
+            if m:
+                keys, tsdf, weight, color = ghost_views(buf, m, self.has_color)
+                buf[: ((3 * m + 3) // 4) * 4].zero_()      # key padding words travel too: keep them defined
+                _lib.check(_lib.lib().mq3d_grid_ghost_select(self._h, int(dest_rank), C.byref(n), _lib.dptr(keys),
+                                                             _lib.dptr(tsdf), _lib.dptr(weight), _lib.dptr(color),
+                                                             _stream()))
+                assert int(n.value) == m
+        return buf, m, self.has_color
 
     # -- K2 -----------------------------------------------------------------------------------------
     def compute_unique_block_coordinates(self, depth, intrinsic, extrinsic, depth_scale: float = 1000.0,

@@ -62,3 +62,46 @@ def test_partition_ownership_rule():
                      for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)}
         assert set(needed) == nb_owners                                # ghost shell = owners of the 26 neighbours
     assert block_needed(1, 2, 3, 0, 1, T)                              # world 1: everything is local
+
+
+class _FakeGrid:
+    """Stands in for VoxelBlockGrid in the gloo test: blocks are rows of CPU tensors."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.blocks = {}                       # key tuple -> (tsdf, weight)
+        for i in range(3 + rank):              # rank r owns 3+r blocks with recognisable values
+            self.blocks[(rank, i, 0)] = (torch.full((4096,), float(10 * rank + i)), torch.full((4096,), float(i)))
+
+    def ghost_select(self, dest):
+        keys = [k for k in self.blocks if k[0] == self.rank and (k[1] + dest) % 2 == 0]   # arbitrary rule
+        k = torch.tensor(keys, dtype=torch.int32).reshape(-1, 3)
+        t = torch.stack([self.blocks[x][0] for x in keys]) if keys else torch.zeros((0, 4096))
+        w = torch.stack([self.blocks[x][1] for x in keys]) if keys else torch.zeros((0, 4096))
+        return k, t, w, None
+
+    def import_blocks(self, keys, tsdf, weight, color=None):
+        for i, key in enumerate(keys.tolist()):
+            self.blocks[tuple(key)] = (tsdf[i].clone(), weight[i].clone())
+
+
+def _ghost_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200.dist import exchange_ghosts
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = _FakeGrid(rank, world)
+    got = exchange_ghosts(g)
+    other = 1 - rank
+    want = [(other, i, 0) for i in range(3 + other) if (i + rank) % 2 == 0]
+    assert got == len(want)
+    for key in want:
+        assert key in g.blocks and float(g.blocks[key][0][7]) == 10 * other + key[1]
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_ghost_exchange_world2(tmp_path):
+    mp.spawn(_ghost_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -79,3 +79,53 @@ def test_partitioned_grids_reproduce_single_grid(cuda_device, oracle, world, til
     assert union_tris == full_tris
     assert union_pts == full_pts
     assert total_blocks >= len(ref)                                        # ghost redundancy factor >= 1
+
+
+@pytest.mark.parametrize("world,tile", [(2, 2), (4, 4)])
+def test_owned_only_integration_plus_ghost_exchange(cuda_device, oracle, world, tile):
+    """integrate_ghosts=False: every rank integrates only its own blocks; after the ghost exchange
+    (emulated here by moving ghost_select payloads between the per-rank grids) each rank holds exactly
+    the blocks -- and bit-exactly the values -- of the redundant-integration mode."""
+    from mq3d_b200.dist import block_needed, tile_owner
+    from mq3d_b200.vbg import VoxelBlockGrid
+    cap = capture(10)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = torch.from_numpy(np.stack([oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i])
+                                     for i in range(len(ds))])).to(cuda_device)
+    full = VoxelBlockGrid(voxel_size=0.02, block_count=2000, device=cuda_device)
+    full.integrate_sequence(lin, K, Ewc, 4.0, 10.0)
+    fk, ft, fw = [x.cpu().numpy() for x in full.export_blocks()[:3]]
+    ref = {tuple(k): (ft[i], fw[i]) for i, k in enumerate(fk.tolist())}
+    fv, fn, ftri, fvk = [x.cpu().numpy() for x in full.extract_triangle_mesh_arrays(1.5, with_keys=True)]
+    full_tris = _tri_keys(fvk, ftri)
+
+    grids, visits = [], 0
+    for rank in range(world):
+        g = VoxelBlockGrid(voxel_size=0.02, block_count=64, device=cuda_device)
+        g.set_partition(rank, world, tile, integrate_ghosts=False)
+        st = g.integrate_sequence(lin, K, Ewc, 4.0, 10.0)
+        visits += st.block_visits
+        k = g.export_blocks()[0].cpu().numpy()
+        assert all(tile_owner(*key, world, tile) == rank for key in k.tolist())     # owned blocks only
+        grids.append(g)
+    assert sum(g.num_blocks() for g in grids) == len(ref)                           # no redundant work at all
+    payloads = {(s, d): grids[s].ghost_select(d) for s in range(world) for d in range(world) if s != d}
+    assert grids[0].ghost_select(0)[0].shape[0] == 0
+    for (s, d), (k, t, w, c) in payloads.items():
+        for key in k.cpu().numpy().tolist():
+            assert tile_owner(*key, world, tile) == s and block_needed(*key, d, world, tile)
+        if k.shape[0]:
+            grids[d].import_blocks(k, t, w, c)
+    union_tris = set()
+    for rank, g in enumerate(grids):
+        k, t, w = [x.cpu().numpy() for x in g.export_blocks()[:3]]
+        assert {tuple(x) for x in k.tolist()} == {key for key in ref if block_needed(*key, rank, world, tile)}
+        for i, key in enumerate(k.tolist()):
+            rt, rw = ref[tuple(key)]
+            assert np.array_equal(w[i], rw) and np.array_equal(t[i].view(np.uint32), rt.view(np.uint32))
+        v, n, tri, vk = [x.cpu().numpy() for x in g.extract_triangle_mesh_arrays(1.5, with_keys=True)]
+        tk = _tri_keys(vk, tri)
+        assert not (tk & union_tris)
+        union_tris |= tk
+    assert union_tris == full_tris
