@@ -31,7 +31,8 @@
 #define R16_EPREF 768    // [3][256] exclusive prefix of popc(edge marks) in (axis, z, y) order
 #define R16_SURF 1536    // [256]    surface cubes of the own rows, bit x
 #define R16_TPREF 1792   // [256]    exclusive prefix of per-row triangle counts
-#define R16_WORDS 2048
+#define R16_SPREF 2048   // [256]    exclusive prefix of per-row surface-cube counts
+#define R16_WORDS 2304
 
 __device__ __forceinline__ int nb_of(int r) { return r < 0 ? 0 : (r > 15 ? 2 : 1); }  // -> d+1
 
@@ -84,86 +85,78 @@ __device__ __forceinline__ int cube_case(unsigned s00, unsigned s10, unsigned s0
 // ------------------------------------------------------------------------------------------------
 // classify
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 5)
+#define MC_CLASSIFY_THREADS 352   // 11 warps: 324 neighbourhood rows in phase A, 289 cube rows in B, 256 own rows in C
+// One CTA per block.  The kernel is latency-bound (one DRAM round trip + a chain of block barriers per
+// 37 KB block), so the chain is kept short: neighbour indices are read by the threads that need them (no
+// staging barrier), the five per-row counts are scanned in registers with warp shuffles (no serial
+// warp-0 scan), three barriers.  (A persistent cp.async-staged variant was measured slower: 0.51 vs 0.30 ms
+// on 17 k blocks.)
+__global__ void __launch_bounds__(MC_CLASSIFY_THREADS, 4)
 k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, const int32_t *__restrict__ block_keys,
-              const int32_t *__restrict__ nb, float weight_thr, Partition part, uint32_t *__restrict__ srow_out,
-              uint16_t *__restrict__ rows16, int32_t *__restrict__ counts) {
+              const int32_t *__restrict__ nb, int64_t n_blocks, float weight_thr, Partition part,
+              uint32_t *__restrict__ srow_out, uint16_t *__restrict__ rows16, int32_t *__restrict__ counts) {
     __shared__ unsigned s_valid[SROW_WORDS], s_sign[SROW_WORDS];
     __shared__ unsigned s_cok[17 * 17];
-    __shared__ int s_nb[27];
-    __shared__ unsigned char s_owned[27];
-    __shared__ unsigned char s_tric[256];
-    __shared__ int s_ecnt[768];
-    __shared__ int s_tcnt[256];
+    __shared__ int s_wtot[8][5];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
-    if (tid < 27) {
-        s_nb[tid] = nb[b * 27 + tid];
-        int dx = tid % 3 - 1, dy = (tid / 3) % 3 - 1, dz = tid / 9 - 1;
-        s_owned[tid] = mq3d_block_owned(block_keys[3 * b] + dx, block_keys[3 * b + 1] + dy, block_keys[3 * b + 2] + dz, part);
-    }
-    s_tric[tid] = MC_TRI_COUNT[tid];
-    for (int i = tid; i < SROW_WORDS; i += 256) {
-        s_valid[i] = 0;
-        s_sign[i] = 0;
-    }
-    __syncthreads();
-    // ---- phase A: load the neighbourhood as bit rows (6 segments per row: x=-1 | 4 x float4 | x=16) ----
-    // Every item is one float4 of tsdf and one of weight (the x=-1 / x=16 columns use the last / first
-    // quad of the neighbour's row); the loop is branch-free up to the shared-memory ORs so that ptxas
-    // keeps the 8 128-bit loads of a round in flight (two rounds of 4 items bound the registers).
-#pragma unroll 1
-    for (int round = 0; round < 2; ++round) {
-        constexpr int N_IT = 4;
-        static_assert(2 * N_IT * 256 >= SROW_WORDS * 6, "phase A does not cover the neighbourhood");
-        float4 tq[N_IT], wq[N_IT];
-#pragma unroll
-        for (int k = 0; k < N_IT; ++k) {
-            const int it = tid + 256 * (k + N_IT * round);
-            const int r = min(it / 6, SROW_WORDS - 1), seg = it % 6;
+    {
+        // ---- phase A: one thread per (y,z) row of the (-1..16)^2 neighbourhood: the 16 interior voxels as
+        // four float4 of tsdf and of weight, the x=-1 / x=16 columns as scalars from the -x / +x neighbour
+        // blocks; branch-free (missing blocks read this block's own row and are masked), 12 loads in flight
+        // per thread, bits assembled in registers (no shared-memory atomics).
+        if (tid < SROW_WORDS) {
+            const int r = tid;
             const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
-            const int nbx = seg == 0 ? 0 : (seg == 5 ? 2 : 1);
-            const int bi = s_nb[nbx + 3 * nb_of(ry) + 9 * nb_of(rz)];
-            const int quad = seg == 0 ? 3 : (seg == 5 ? 0 : seg - 1);
-            // missing neighbour / tail item: read this block's own row instead (result is discarded)
-            const int64_t base = (int64_t)(bi < 0 ? (int)b : bi) * MQ3D_RES3 + ((rz & 15) * 16 + (ry & 15)) * 16;
-            tq[k] = __ldg(reinterpret_cast<const float4 *>(tsdf + base) + quad);
-            wq[k] = __ldg(reinterpret_cast<const float4 *>(weight + base) + quad);
-        }
+            const int k0 = 3 * nb_of(ry) + 9 * nb_of(rz);
+            const int bm = __ldg(nb + b * 27 + k0), b0 = __ldg(nb + b * 27 + k0 + 1), bp = __ldg(nb + b * 27 + k0 + 2);
+            const int ro = ((rz & 15) * 16 + (ry & 15)) * 16;
+            const float *t0 = tsdf + (int64_t)(b0 < 0 ? (int)b : b0) * MQ3D_RES3 + ro;
+            const float *w0 = weight + (int64_t)(b0 < 0 ? (int)b : b0) * MQ3D_RES3 + ro;
+            const int64_t om = (int64_t)(bm < 0 ? (int)b : bm) * MQ3D_RES3 + ro + 15;
+            const int64_t op = (int64_t)(bp < 0 ? (int)b : bp) * MQ3D_RES3 + ro;
+            float4 tq[4], wq[4];
 #pragma unroll
-        for (int k = 0; k < N_IT; ++k) {
-            const int it = tid + 256 * (k + N_IT * round);
-            const int r = min(it / 6, SROW_WORDS - 1), seg = it % 6;
-            const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
-            const int nbx = seg == 0 ? 0 : (seg == 5 ? 2 : 1);
-            const bool live = it < SROW_WORDS * 6 && s_nb[nbx + 3 * nb_of(ry) + 9 * nb_of(rz)] >= 0;
-            const float4 t = tq[k], w = wq[k];
-            // Open3D rejects `w <= thr`
-            unsigned v4 = (w.x > weight_thr ? 1u : 0u) | (w.y > weight_thr ? 2u : 0u) | (w.z > weight_thr ? 4u : 0u) |
-                          (w.w > weight_thr ? 8u : 0u);
-            unsigned s4 = (t.x < 0.0f ? 1u : 0u) | (t.y < 0.0f ? 2u : 0u) | (t.z < 0.0f ? 4u : 0u) | (t.w < 0.0f ? 8u : 0u);
-            unsigned vb, sb;
-            if (seg == 0) { vb = v4 >> 3; sb = s4 >> 3; }                              // x = -1  -> bit 0
-            else if (seg == 5) { vb = (v4 & 1u) << 17; sb = (s4 & 1u) << 17; }          // x = 16  -> bit 17
-            else { vb = v4 << (4 * seg - 3); sb = s4 << (4 * seg - 3); }                // x = 4(seg-1).. -> bits 1+..
-            if (live && vb) atomicOr(&s_valid[r], vb);
-            if (live && sb) atomicOr(&s_sign[r], sb);
+            for (int q = 0; q < 4; ++q) {
+                tq[q] = __ldg(reinterpret_cast<const float4 *>(t0) + q);
+                wq[q] = __ldg(reinterpret_cast<const float4 *>(w0) + q);
+            }
+            const float tm = __ldg(tsdf + om), wm = __ldg(weight + om), tp = __ldg(tsdf + op), wp = __ldg(weight + op);
+            unsigned vrow = 0, srow = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // Open3D rejects `w <= thr`
+                vrow |= ((wq[q].x > weight_thr ? 1u : 0u) | (wq[q].y > weight_thr ? 2u : 0u) | (wq[q].z > weight_thr ? 4u : 0u) |
+                         (wq[q].w > weight_thr ? 8u : 0u)) << (1 + 4 * q);
+                srow |= ((tq[q].x < 0.0f ? 1u : 0u) | (tq[q].y < 0.0f ? 2u : 0u) | (tq[q].z < 0.0f ? 4u : 0u) |
+                         (tq[q].w < 0.0f ? 8u : 0u)) << (1 + 4 * q);
+            }
+            if (b0 < 0) vrow = srow = 0;
+            if (bm >= 0) { vrow |= (wm > weight_thr ? 1u : 0u); srow |= (tm < 0.0f ? 1u : 0u); }
+            if (bp >= 0) { vrow |= (wp > weight_thr ? 1u : 0u) << 17; srow |= (tp < 0.0f ? 1u : 0u) << 17; }
+            s_valid[r] = vrow;
+            s_sign[r] = srow;
+            srow_out[b * SROW_WORDS + r] = srow;
         }
-    }
-    __syncthreads();
+        __syncthreads();
     // ---- phase B: valid (and owned) cubes of the cube rows (cy,cz) in -1..15, bit i <-> cube x = i-1 ----
-    for (int c = tid; c < 17 * 17; c += 256) {
+    if (tid < 17 * 17) {
+        const int c = tid;
         const int cy = c % 17, cz = c / 17;      // region row index of the cube's low corner (cube y = cy-1)
         const unsigned m = s_valid[cz * ROW_R + cy] & s_valid[cz * ROW_R + cy + 1] & s_valid[(cz + 1) * ROW_R + cy] &
                            s_valid[(cz + 1) * ROW_R + cy + 1];
         unsigned ok = m & (m >> 1) & 0x1FFFFu;
-        const int ky = cy == 0 ? 0 : 1, kz = cz == 0 ? 0 : 1;     // cube y/z = -1 -> neighbour block -1
-        const unsigned own = (s_owned[0 + 3 * ky + 9 * kz] ? 1u : 0u) | (s_owned[1 + 3 * ky + 9 * kz] ? 0x1FFFEu : 0u);
-        s_cok[c] = ok & own;
+        if (part.world > 1) {                    // cubes count only in owned blocks; cube y/z = -1 -> block -1
+            const int kx = block_keys[3 * b], ky = block_keys[3 * b + 1] + (cy == 0 ? -1 : 0),
+                      kz = block_keys[3 * b + 2] + (cz == 0 ? -1 : 0);
+            ok &= (mq3d_block_owned(kx - 1, ky, kz, part) ? 1u : 0u) | (mq3d_block_owned(kx, ky, kz, part) ? 0x1FFFEu : 0u);
+        }
+        s_cok[c] = ok;
     }
     __syncthreads();
     // ---- phase C: one thread per own row (y,z): edge marks, surface cubes, triangle count ----
-    {
+    int cnt[5] = {0, 0, 0, 0, 0};   // popc(x marks), popc(y marks), popc(z marks), triangles, surface cubes
+    if (tid < 256) {
         const int y = tid & 15, z = tid >> 4;
         const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
         const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
@@ -178,39 +171,55 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
         // surface cubes of this row: valid cubes whose 8 corner signs are not all equal
         const unsigned same4 = ~((s00 ^ s10) | (s00 ^ s01) | (s00 ^ s11));
         const unsigned flat = same4 & (same4 >> 1) & ~(s00 ^ (s00 >> 1));
-        unsigned surf = (c00 & ~flat) >> 1 & 0xFFFFu;
+        const unsigned surf = (c00 & ~flat) >> 1 & 0xFFFFu;
         int ntri = 0;
-        for (unsigned m = surf; m; m &= m - 1) {
-            const int x = __ffs(m) - 1;
-            ntri += s_tric[cube_case(s00, s10, s01, s11, x + 1)];
-        }
+        for (unsigned m = surf; m; m &= m - 1) ntri += MC_TRI_COUNT[cube_case(s00, s10, s01, s11, __ffs(m))];
         uint16_t *r16 = rows16 + b * R16_WORDS;
         r16[R16_EMASK + tid] = (uint16_t)mx;
         r16[R16_EMASK + 256 + tid] = (uint16_t)my;
         r16[R16_EMASK + 512 + tid] = (uint16_t)mz;
         r16[R16_SURF + tid] = (uint16_t)surf;
-        s_ecnt[tid] = __popc(mx);
-        s_ecnt[256 + tid] = __popc(my);
-        s_ecnt[512 + tid] = __popc(mz);
-        s_tcnt[tid] = ntri;
+        cnt[0] = __popc(mx); cnt[1] = __popc(my); cnt[2] = __popc(mz); cnt[3] = ntri; cnt[4] = __popc(surf);
+    }
+    // block-wide exclusive scans of the five counts over the 256 rows: warp shuffles + 8 warp totals
+    int incl[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        int v = cnt[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += t;
+        }
+        incl[k] = v;
+        if (lane == 31 && warp < 8) s_wtot[warp][k] = v;
     }
     __syncthreads();
-    if (warp == 0) {
-        const int nv = warp0_exclusive_scan(s_ecnt, 768, lane);
-        const int nt = warp0_exclusive_scan(s_tcnt, 256, lane);
-        if (lane == 0) {
-            counts[2 * b] = nv;
-            counts[2 * b + 1] = nt;
+    if (tid < 256) {
+        int base[5], tot[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            base[k] = 0;
+            tot[k] = 0;
+            for (int w = 0; w < 8; ++w) {
+                const int t = s_wtot[w][k];
+                if (w < warp) base[k] += t;
+                tot[k] += t;
+            }
+        }
+        uint16_t *r16 = rows16 + b * R16_WORDS;
+        // vertex numbering is axis-major: x edges, then y edges, then z edges
+        r16[R16_EPREF + tid] = (uint16_t)(base[0] + incl[0] - cnt[0]);
+        r16[R16_EPREF + 256 + tid] = (uint16_t)(tot[0] + base[1] + incl[1] - cnt[1]);
+        r16[R16_EPREF + 512 + tid] = (uint16_t)(tot[0] + tot[1] + base[2] + incl[2] - cnt[2]);
+        r16[R16_TPREF + tid] = (uint16_t)(base[3] + incl[3] - cnt[3]);
+        r16[R16_SPREF + tid] = (uint16_t)(base[4] + incl[4] - cnt[4]);
+        if (tid == 0) {
+            counts[2 * b] = tot[0] + tot[1] + tot[2];
+            counts[2 * b + 1] = tot[3];
         }
     }
-    __syncthreads();
-    {
-        uint16_t *r16 = rows16 + b * R16_WORDS;
-        r16[R16_EPREF + tid] = (uint16_t)s_ecnt[tid];
-        r16[R16_EPREF + 256 + tid] = (uint16_t)s_ecnt[256 + tid];
-        r16[R16_EPREF + 512 + tid] = (uint16_t)s_ecnt[512 + tid];
-        r16[R16_TPREF + tid] = (uint16_t)s_tcnt[tid];
-        for (int i = tid; i < SROW_WORDS; i += 256) srow_out[b * SROW_WORDS + i] = s_sign[i];
+        // (the barrier at the top of the next iteration orders this block's shared-memory reads before
+        //  the next block's writes)
     }
 }
 
@@ -338,7 +347,8 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
     if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(rows16 + b * R16_WORDS);
-        reinterpret_cast<uint4 *>(s_r16)[tid] = __ldg(src + tid);       // 256 x 16 B = 4 KB
+        reinterpret_cast<uint4 *>(s_r16)[tid] = __ldg(src + tid);       // 288 x 16 B = 4.5 KB
+        if (tid < R16_WORDS / 8 - 256) reinterpret_cast<uint4 *>(s_r16)[256 + tid] = __ldg(src + 256 + tid);
     }
     const bool do_tris = nt > 0 && tris != nullptr;
     if (do_tris) {
@@ -380,24 +390,17 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
     }
     // ---- triangles: one thread per surface cube (row by binary search over the per-row cube counts) ----
     if (do_tris) {
-        __shared__ int s_sp[256];
-        s_sp[tid] = __popc((unsigned)s_r16[R16_SURF + tid]);
-        __syncthreads();
-        int ncubes = 0;
-        if (tid < 32) ncubes = warp0_exclusive_scan(s_sp, 256, tid);
-        __shared__ int s_ncubes;
-        if (tid == 0) s_ncubes = ncubes;
-        __syncthreads();
-        ncubes = s_ncubes;
+        const uint16_t *s_sp = s_r16 + R16_SPREF;      // no barrier between the vertex and the triangle phase
+        const int ncubes = (int)s_sp[255] + __popc((unsigned)s_r16[R16_SURF + 255]);
         for (int j = tid; j < ncubes; j += 256) {
             int lo = 0, hi = 255;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (s_sp[mid] <= j) lo = mid; else hi = mid - 1;
+                if ((int)s_sp[mid] <= j) lo = mid; else hi = mid - 1;
             }
             const int row = lo, y = row & 15, z = row >> 4;
             const unsigned surf = s_r16[R16_SURF + row];
-            const int kth = j - s_sp[row];
+            const int kth = j - (int)s_sp[row];
             const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
             const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
             int64_t tbase = toff + s_r16[R16_TPREF + row];
@@ -581,7 +584,7 @@ extern "C" int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int
     MQ3D_TRY(mc_prepare(g, st));
     int64_t n = g->mc_blocks;
     if (n > 0) {
-        k_mc_classify<<<(unsigned)n, 256, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, weight_threshold, g->part,
+        k_mc_classify<<<(unsigned)n, MC_CLASSIFY_THREADS, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, n, weight_threshold, g->part,
                                                    g->mc_emask, g->mc_eprefix, g->mc_counts);
         MQ3D_CUDA(cudaGetLastError());
     }
