@@ -77,11 +77,14 @@ struct HashView {
 };
 
 #ifdef __CUDACC__
-// insert-or-find; returns slot.  `fresh` is set when this call claimed the slot.
+#define MQ3D_NO_SLOT 0xFFFFFFFFu
+// insert-or-find; returns slot, or MQ3D_NO_SLOT when the table is full (the probe sequence wrapped
+// around) -- the host then grows the table and repeats the launch.  `fresh` is set when this call
+// claimed the slot.
 __device__ __forceinline__ uint32_t hash_insert(const HashView &h, uint64_t key, bool &fresh) {
     uint32_t slot = mq3d_hash64(key) & h.mask;
     fresh = false;
-    for (;;) {
+    for (uint32_t probes = 0; probes <= h.mask; ++probes) {
         unsigned long long cur = h.keys[slot];
         if (cur == key) return slot;
         if (cur == MQ3D_EMPTY_KEY) {
@@ -94,16 +97,18 @@ __device__ __forceinline__ uint32_t hash_insert(const HashView &h, uint64_t key,
         }
         slot = (slot + 1) & h.mask;
     }
+    return MQ3D_NO_SLOT;
 }
 // lookup only; returns slot or 0xFFFFFFFF
 __device__ __forceinline__ uint32_t hash_find(const HashView &h, uint64_t key) {
     uint32_t slot = mq3d_hash64(key) & h.mask;
-    for (;;) {
+    for (uint32_t probes = 0; probes <= h.mask; ++probes) {
         unsigned long long cur = h.keys[slot];
         if (cur == key) return slot;
         if (cur == MQ3D_EMPTY_KEY) return 0xFFFFFFFFu;
         slot = (slot + 1) & h.mask;
     }
+    return 0xFFFFFFFFu;
 }
 #endif
 

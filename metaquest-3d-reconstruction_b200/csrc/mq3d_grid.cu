@@ -38,7 +38,7 @@ __global__ void k_rehash(HashView src, int64_t src_size, HashView dst) {
     if (k == MQ3D_EMPTY_KEY) return;
     bool fresh;
     uint32_t s = hash_insert(dst, k, fresh);
-    dst.vals[s] = src.vals[i];
+    if (s != MQ3D_NO_SLOT) dst.vals[s] = src.vals[i];   // (dst is at most half full: cannot fail)
 }
 
 // block_keys[val] = unpack(key) for every occupied slot (after pool growth)
@@ -446,6 +446,10 @@ __global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int 
     if (integrating ? !MQ3D_INTEGRATES(x, y, z, part) : !mq3d_block_needed(x, y, z, part)) return;
     bool fresh;
     uint32_t s = hash_insert(h, mq3d_pack_key(x, y, z), fresh);
+    if (s == MQ3D_NO_SLOT) {   // cannot happen: the host reserved room for every key beforehand
+        *bad_key_flag = 2;
+        return;
+    }
     if (fresh) {
         int b = atomicAdd(n_blocks, 1);
         h.vals[s] = b;
