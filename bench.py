@@ -186,7 +186,7 @@ def run_gpu(args):
         t_a = time.perf_counter()
         if world > 1 and args.ghosts == "exchange":
             from mq3d_b200.dist import exchange_ghosts
-            exchange_ghosts(vbg, rank, world)        # owners -> ghost shells, once, before extraction
+            exchange_ghosts(vbg, rank, world, timings=xch_phases)   # owners -> ghost shells, once, before extraction
             torch.cuda.synchronize()
         t_b = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,6 +203,7 @@ def run_gpu(args):
         return st, (v, nrm, t), (e0, e1)
 
     mgpu_ms = {"exchange": [], "gather": []}
+    xch_phases = {} if os.environ.get("MQ3D_TRACE") else None      # per-phase exchange times (diagnostics)
 
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -226,6 +227,10 @@ def run_gpu(args):
     mc_list = [a.elapsed_time(b) for a, b in mc_events]
     if os.environ.get("MQ3D_TRACE"):
         print("[bench] per-step mc ms:", [round(x, 3) for x in mc_list], file=sys.stderr)
+        if xch_phases:
+            calls = args.steps + args.warmup
+            print(f"[bench r{rank}] exchange phases ms/step:", {k: round(v / calls, 3) for k, v in xch_phases.items()},
+                  file=sys.stderr)
     mc_ms = float(np.mean(mc_list))
     st = stats[-1]
     integ_ms = float(np.mean([s.integrate_ms for s in stats]))
@@ -238,12 +243,23 @@ def run_gpu(args):
 
     def step_e2e():
         vbg.reset()
+        if world == 1:
+            integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params, colors_host=col_host,
+                             Kc=wl["Kc"])
+            return extract_mesh_to_host(vbg, cfg["weight_thr"])
+        # N > 1: every rank uploads 1/N of each chunk over its own PCIe link, NCCL all-gather completes the
+        # chunk over NVLink; per-rank meshes are gathered on rank 0, which reads the whole mesh back
+        from mq3d_b200.dist import exchange_ghosts, gather_mesh
         integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params, colors_host=col_host,
-                         Kc=wl["Kc"])
-        if world > 1 and args.ghosts == "exchange":
-            from mq3d_b200.dist import exchange_ghosts
+                         Kc=wl["Kc"], shard=(rank, world))
+        if args.ghosts == "exchange":
             exchange_ghosts(vbg, rank, world)
-        return extract_mesh_to_host(vbg, cfg["weight_thr"])
+        v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
+        gv, gn, gt, _ = gather_mesh(v, nrm, t, dst=0)
+        if rank != 0:
+            torch.cuda.synchronize()
+            return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)
+        return gv.cpu().numpy(), gn.cpu().numpy(), gt.cpu().numpy()
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -273,6 +289,8 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
+    if (hv.shape[0], ht.shape[0]) != (V, T):
+        raise SystemExit(f"end-to-end mesh {hv.shape[0]}/{ht.shape[0]} differs from the device-resident run {V}/{T}")
     ms_per_step = total_ms / args.steps
     frames_per_s = n / (ms_per_step * 1e-3)
     bytes_per_visit = 40 if color else 16

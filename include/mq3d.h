@@ -86,6 +86,10 @@ int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int tile_blocks);
 int mq3d_grid_set_ghost_mode(mq3d_grid *g, int integrate_ghosts);
 int mq3d_grid_ghost_select(mq3d_grid *g, int dest_rank, int64_t *n_out, int32_t *keys_dev, float *tsdf_dev,
                            float *weight_dev, float *color_dev, void *stream);
+/* Ghost block counts for every destination rank in one pass (counts_out: host int64[world], entry of the
+ * own rank is 0).  Passing a count obtained here as *n_out to mq3d_grid_ghost_select (with buffers) makes
+ * that call fully asynchronous: no host synchronisation, payload valid in stream order. */
+int mq3d_grid_ghost_counts(mq3d_grid *g, int64_t *counts_out, void *stream);
 
 /* ---- K1: raw NDC depth -> linear metres + confidence mask -----------------------------------
  * Replaces DepthDataIO.load_depth_map's convert_depth_to_linear + is_depth_map_valid
@@ -160,6 +164,13 @@ int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *normals_dev
 int mq3d_extract_points_count(mq3d_grid *g, float weight_threshold, int64_t *n_points, void *stream);
 int mq3d_extract_points_fill(mq3d_grid *g, float *points_dev, float *normals_dev,
                              int32_t *point_keys_dev, void *stream);
+/* Vertex / point colours of a grid with the colour attribute (north-star row A3c; Open3D's colour branch
+ * of ExtractTriangleMesh / ExtractPointCloud, what mesh.vertex.colors / pcd.point.colors hold after
+ * reconstruct_scene.py:90,105-108 on a coloured grid): float32 [V][3] in [0,1] =
+ * ((1 - ratio) * c_owner + ratio * c_neighbour) / 255, same order as the matching *_fill.  Valid
+ * between the matching *_count and the next change of the grid. */
+int mq3d_extract_mesh_colors(mq3d_grid *g, float *colors_dev, void *stream);
+int mq3d_extract_points_colors(mq3d_grid *g, float *colors_dev, void *stream);
 
 /* ---- K4: multi-view depth confidence --------------------------------------------------------
  * Replaces build_confidence_map over all reference frames of one side

@@ -222,7 +222,8 @@ struct mq3d_grid {
     FrameParams *frame_params_dev;  // [MQ3D_MAX_BATCH]
     int32_t *idx_scratch;  // per-frame integrate: block index per key
     int64_t idx_scratch_size;
-    int *pinned_host;     // pinned int[8] for async readbacks
+    int *ghost_cnt_dev, *ghost_cnt_host;  // [64] per-destination ghost counts (device / pinned)
+    int *pinned_host;    // pinned int[8] for async readbacks
     int64_t *pinned_host64;            // two pinned int64 (tail of pinned_host) for the MC totals
     int *frame_counts_dev;             // [MQ3D_MAX_BATCH]
     unsigned long long *stat_dev;      // [2]

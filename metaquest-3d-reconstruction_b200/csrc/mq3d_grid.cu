@@ -196,6 +196,8 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->color_lut);
     cudaFree(g->frame_params_dev);
     cudaFree(g->idx_scratch);
+    cudaFree(g->ghost_cnt_dev);
+    if (g->ghost_cnt_host) cudaFreeHost(g->ghost_cnt_host);
     if (g->pinned_host) cudaFreeHost(g->pinned_host);
     cudaFree(g->frame_counts_dev);
     cudaFree(g->stat_dev);
@@ -273,12 +275,72 @@ __global__ void k_ghost_gather(const int32_t *__restrict__ idx, const int32_t *_
     }
 }
 
+// per-destination ghost counts in one pass (counts[d] = owned blocks that rank d keeps as ghosts)
+__global__ void k_ghost_counts(const int32_t *__restrict__ block_keys, int64_t n, Partition part, int *__restrict__ counts) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    int x = block_keys[3 * b], y = block_keys[3 * b + 1], z = block_keys[3 * b + 2];
+    if (!mq3d_block_owned(x, y, z, part)) return;
+    unsigned long long seen = 0;   // destinations already counted for this block (world <= 64)
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                int d = mq3d_tile_owner(x + dx, y + dy, z + dz, part);
+                if (d != part.rank && !((seen >> d) & 1ull)) {
+                    seen |= 1ull << d;
+                    atomicAdd(&counts[d], 1);
+                }
+            }
+}
+
+extern "C" int mq3d_grid_ghost_counts(mq3d_grid *g, int64_t *counts_out, void *stream) {
+    MQ3D_REQUIRE(g && counts_out, "null argument");
+    MQ3D_REQUIRE(g->part.world <= 64, "ghost exchange supports at most 64 ranks");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    const int64_t n = g->n_blocks_host;
+    for (int d = 0; d < g->part.world; ++d) counts_out[d] = 0;
+    if (n == 0 || g->part.world <= 1) return MQ3D_OK;
+    if (!g->ghost_cnt_dev) {
+        MQ3D_CUDA(cudaMalloc(&g->ghost_cnt_dev, sizeof(int) * 64));
+        MQ3D_CUDA(cudaMallocHost(&g->ghost_cnt_host, sizeof(int) * 64));
+    }
+    if (n > g->idx_scratch_size) {   // so the per-destination fills can run without further host syncs
+        cudaFree(g->idx_scratch);
+        g->idx_scratch = nullptr;
+        g->idx_scratch_size = 0;
+        MQ3D_CUDA(cudaMalloc(&g->idx_scratch, sizeof(int32_t) * next_pow2(n)));
+        g->idx_scratch_size = next_pow2(n);
+    }
+    MQ3D_CUDA(cudaMemsetAsync(g->ghost_cnt_dev, 0, sizeof(int) * 64, st));
+    k_ghost_counts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->block_keys, n, g->part, g->ghost_cnt_dev);
+    MQ3D_CUDA(cudaGetLastError());
+    MQ3D_CUDA(cudaMemcpyAsync(g->ghost_cnt_host, g->ghost_cnt_dev, sizeof(int) * 64, cudaMemcpyDeviceToHost, st));
+    MQ3D_CUDA(cudaStreamSynchronize(st));
+    for (int d = 0; d < g->part.world; ++d) counts_out[d] = g->ghost_cnt_host[d];
+    return MQ3D_OK;
+}
+
 extern "C" int mq3d_grid_ghost_select(mq3d_grid *g, int dest_rank, int64_t *n_out, int32_t *keys_dev, float *tsdf_dev,
                                       float *weight_dev, float *color_dev, void *stream) {
     MQ3D_REQUIRE(g && n_out, "null argument");
     MQ3D_REQUIRE(dest_rank >= 0 && dest_rank < g->part.world, "bad destination rank");
     MQ3D_TRY(mq3d_set_device(g->device));
     cudaStream_t st = as_stream(stream);
+    const int64_t expected = *n_out;   // > 0 with buffers: count known from mq3d_grid_ghost_counts -> no host sync
+    if (keys_dev && expected > 0 && g->n_blocks_host > 0 && dest_rank != g->part.rank &&
+        g->n_blocks_host <= g->idx_scratch_size) {
+        MQ3D_REQUIRE(tsdf_dev && weight_dev, "null ghost payload buffers");
+        const int64_t nb = g->n_blocks_host;
+        MQ3D_CUDA(cudaMemsetAsync(g->counter_dev + 5, 0, sizeof(int), st));
+        k_ghost_select<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(g->block_keys, nb, g->part, dest_rank,
+                                                                     g->counter_dev + 5, g->idx_scratch);
+        k_ghost_gather<<<(unsigned)expected, 256, 0, st>>>(g->idx_scratch, g->block_keys, g->tsdf, g->weight, g->color,
+                                                           keys_dev, tsdf_dev, weight_dev, color_dev);
+        MQ3D_CUDA(cudaGetLastError());
+        return MQ3D_OK;
+    }
     MQ3D_TRY(mq3d_grid_sync_count(g, st));
     const int64_t n = g->n_blocks_host;
     *n_out = 0;

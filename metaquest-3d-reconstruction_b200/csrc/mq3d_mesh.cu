@@ -291,9 +291,11 @@ __device__ __forceinline__ void write_vertex(float *__restrict__ verts, float *_
                                              const float *no, const float *ne) {
     float rx = __fmul_rn(ratio, e == 0 ? 1.0f : 0.0f), ry = __fmul_rn(ratio, e == 1 ? 1.0f : 0.0f),
           rz = __fmul_rn(ratio, e == 2 ? 1.0f : 0.0f);
-    verts[3 * id + 0] = __fmul_rn(vs, __fadd_rn((float)gx, rx));
-    verts[3 * id + 1] = __fmul_rn(vs, __fadd_rn((float)gy, ry));
-    verts[3 * id + 2] = __fmul_rn(vs, __fadd_rn((float)gz, rz));
+    if (verts) {
+        verts[3 * id + 0] = __fmul_rn(vs, __fadd_rn((float)gx, rx));
+        verts[3 * id + 1] = __fmul_rn(vs, __fadd_rn((float)gy, ry));
+        verts[3 * id + 2] = __fmul_rn(vs, __fadd_rn((float)gz, rz));
+    }
     if (vkeys) {
         vkeys[4 * id] = gx; vkeys[4 * id + 1] = gy; vkeys[4 * id + 2] = gz; vkeys[4 * id + 3] = e;
     }
@@ -326,6 +328,51 @@ __device__ __forceinline__ void get_normal_g(const float *__restrict__ tsdf, con
     if (p >= 0 && m >= 0) n[1] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
     p = nb_lin(s_nb, x, y, z + 1); m = nb_lin(s_nb, x, y, z - 1);
     if (p >= 0 && m >= 0) n[2] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
+}
+
+// Open3D's colour branch of ExtractTriangleMesh / ExtractPointCloud: ((1-ratio)*c_o + ratio*c_e) / 255
+// on the float32 colour attribute (voxel linear indices lo / le into the [n][4096][3] pool)
+__device__ __forceinline__ void write_color(float *__restrict__ out, int64_t id, const float *__restrict__ color,
+                                            int64_t lo, int64_t le, float ratio) {
+    const float om = __fsub_rn(1.0f, ratio);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out[3 * id + c] = __fdiv_rn(__fadd_rn(__fmul_rn(om, __ldg(color + 3 * lo + c)), __fmul_rn(ratio, __ldg(color + 3 * le + c))),
+                                    255.0f);
+}
+
+// vertex colours of the mesh laid out by k_mc_classify / k_scan_counts (same vertex order as k_mc_emit)
+__global__ void __launch_bounds__(256)
+k_mc_colors(const float *__restrict__ tsdf, const float *__restrict__ color, const int32_t *__restrict__ nb,
+            const uint16_t *__restrict__ rows16, const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+            float *__restrict__ vcolors) {
+    __shared__ int s_nb[27];
+    __shared__ uint16_t s_ep[768], s_em[768];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const int nv = counts[2 * b];
+    if (nv == 0) return;
+    if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
+    for (int i = tid; i < 768; i += 256) {
+        s_ep[i] = rows16[b * R16_WORDS + R16_EPREF + i];
+        s_em[i] = rows16[b * R16_WORDS + R16_EMASK + i];
+    }
+    __syncthreads();
+    const int64_t voff = offsets[2 * b];
+    for (int j = tid; j < nv; j += 256) {
+        int lo = 0, hi = 767;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)s_ep[mid] <= j) lo = mid; else hi = mid - 1;
+        }
+        const int item = lo, e = item >> 8, row = item & 255, y = row & 15, z = row >> 4;
+        const int x = (int)__fns((unsigned)s_em[item], 0, j - (int)s_ep[item] + 1);
+        const int64_t lin_o = b * MQ3D_RES3 + row * 16 + x;
+        const int64_t lin_e = nb_lin(s_nb, x + (e == 0), y + (e == 1), z + (e == 2));
+        const float to = __ldg(tsdf + lin_o), te = __ldg(tsdf + lin_e);
+        const float ratio = __fdiv_rn(__fsub_rn(0.0f, to), __fsub_rn(te, to));
+        write_color(vcolors, voff + j, color, lin_o, lin_e, ratio);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +511,7 @@ __global__ void __launch_bounds__(256)
 k_points(const float *__restrict__ tsdf, const float *__restrict__ weight, const int32_t *__restrict__ block_keys,
          const int32_t *__restrict__ nb, float weight_thr, Partition part, int32_t *__restrict__ counts,
          const int64_t *__restrict__ offsets, float vs, float *__restrict__ points, float *__restrict__ normals,
-         int32_t *__restrict__ pkeys) {
+         int32_t *__restrict__ pkeys, const float *__restrict__ color, float *__restrict__ pcolors) {
     __shared__ float s_t[TS_R * TS_R * TS_R];
     __shared__ int s_nb[27];
     __shared__ int s_sum[128];
@@ -531,7 +578,8 @@ k_points(const float *__restrict__ tsdf, const float *__restrict__ weight, const
             float ti = TS(ex, ey, ez);
             float ratio = __fdiv_rn(__fsub_rn(0.0f, to), __fsub_rn(ti, to));
             get_normal(s_t, s_nb, ex, ey, ez, ni);
-            write_vertex(points, normals, pkeys, id, vs, kx * 16 + x, ky * 16 + y, kz * 16 + z, e, ratio, no, ni);
+            if (points) write_vertex(points, normals, pkeys, id, vs, kx * 16 + x, ky * 16 + y, kz * 16 + z, e, ratio, no, ni);
+            if (pcolors) write_color(pcolors, id, color, b * MQ3D_RES3 + v, nb_lin(s_nb, ex, ey, ez), ratio);
             ++id;
         }
     }
@@ -625,7 +673,8 @@ extern "C" int mq3d_extract_points_count(mq3d_grid *g, float weight_threshold, i
     int64_t n = g->mc_blocks;
     if (n > 0) {
         k_points<false><<<(unsigned)n, 256, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, weight_threshold, g->part,
-                                                     g->mc_counts, nullptr, g->voxel_size, nullptr, nullptr, nullptr);
+                                                     g->mc_counts, nullptr, g->voxel_size, nullptr, nullptr, nullptr, nullptr,
+                                                     nullptr);
         MQ3D_CUDA(cudaGetLastError());
     }
     int64_t dummy;
@@ -649,7 +698,44 @@ extern "C" int mq3d_extract_points_fill(mq3d_grid *g, float *points_dev, float *
     if (g->mc_blocks > 0 && g->mc_V > 0) {
         k_points<true><<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, g->mc_weight_thr,
                                                                g->part, g->mc_counts, g->mc_offsets, g->voxel_size,
-                                                               points_dev, normals_dev, point_keys_dev);
+                                                               points_dev, normals_dev, point_keys_dev, nullptr, nullptr);
+        MQ3D_CUDA(cudaGetLastError());
+    }
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_extract_mesh_colors(mq3d_grid *g, float *colors_dev, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    if (g->mc_state != 1) {
+        mq3d_set_error("extract_mesh_colors called without a preceding extract_mesh_count on an unchanged grid");
+        return MQ3D_ERR_STATE;
+    }
+    MQ3D_REQUIRE(g->color != nullptr, "grid has no colour attribute");
+    MQ3D_REQUIRE(g->mc_V == 0 || colors_dev, "null colour buffer");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    if (g->mc_blocks > 0 && g->mc_V > 0) {
+        k_mc_colors<<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->color, g->mc_nb, g->mc_eprefix, g->mc_counts,
+                                                            g->mc_offsets, colors_dev);
+        MQ3D_CUDA(cudaGetLastError());
+    }
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_extract_points_colors(mq3d_grid *g, float *colors_dev, void *stream) {
+    MQ3D_REQUIRE(g != nullptr, "null grid");
+    if (g->mc_state != 2) {
+        mq3d_set_error("extract_points_colors called without a preceding extract_points_count on an unchanged grid");
+        return MQ3D_ERR_STATE;
+    }
+    MQ3D_REQUIRE(g->color != nullptr, "grid has no colour attribute");
+    MQ3D_REQUIRE(g->mc_V == 0 || colors_dev, "null colour buffer");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    if (g->mc_blocks > 0 && g->mc_V > 0) {
+        k_points<true><<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, g->mc_weight_thr,
+                                                               g->part, g->mc_counts, g->mc_offsets, g->voxel_size,
+                                                               nullptr, nullptr, nullptr, g->color, colors_dev);
         MQ3D_CUDA(cudaGetLastError());
     }
     return MQ3D_OK;

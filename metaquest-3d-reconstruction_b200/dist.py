@@ -58,11 +58,11 @@ def broadcast_frames(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     return t
 
 
-def _pack_ghosts(vbg, dest: int):
+def _pack_ghosts(vbg, dest: int, count: Optional[int] = None):
     """(flat float32 payload, block count, has_color) for `dest`; layout = vbg.ghost_packed_len/ghost_views."""
     from .vbg import ghost_packed_len, ghost_views
     if hasattr(vbg, "ghost_select_packed"):
-        return vbg.ghost_select_packed(dest)
+        return vbg.ghost_select_packed(dest) if count is None else vbg.ghost_select_packed(dest, count)
     k, t, w, c = vbg.ghost_select(dest)
     m, has_color = int(k.shape[0]), c is not None
     buf = torch.zeros(ghost_packed_len(m, has_color), dtype=torch.float32, device=k.device)
@@ -73,7 +73,8 @@ def _pack_ghosts(vbg, dest: int):
     return buf, m, has_color
 
 
-def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None) -> int:
+def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None,
+                    timings: Optional[dict] = None) -> int:
     """Owned-only integration mode: fetch the ghost shell from the owners.  One all-gather of the
     [world x world] block-count matrix, then one packed send/recv per rank pair (keys | tsdf | weight |
     colour in a single buffer), then one import.  `vbg` needs ghost_select(dest) (or ghost_select_packed)
@@ -86,18 +87,43 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
         rank, world = dist.get_rank(), dist.get_world_size()
     if world == 1:
         return 0
-    outgoing = {d: _pack_ghosts(vbg, d) for d in range(world) if d != rank}
-    first = next(iter(outgoing.values()))
-    dev, has_color = first[0].device, first[2]
-    send_n = torch.zeros(world, dtype=torch.int64, device=dev)
-    for d, (_, m, _) in outgoing.items():
-        send_n[d] = m
-    matrix = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(matrix, send_n)                       # matrix[src][dst] = blocks src sends to dst
-    recv_n = [int(matrix[p][rank]) for p in range(world)]
+    import time as _time
+    t_last = [_time.perf_counter()]
+
+    def lap(name):          # optional phase timing (synchronises; diagnostics only)
+        if timings is not None:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            now = _time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+
+    if hasattr(vbg, "ghost_counts"):
+        # one counting kernel + one sync for all destinations; the count matrix travels while the
+        # payloads are being packed (asynchronous selects, no further host syncs)
+        counts = vbg.ghost_counts()
+        lap("counts")
+        dev = torch.device(vbg.device)
+        send_n = torch.tensor(counts, dtype=torch.int64).to(dev, non_blocking=True)
+        matrix = torch.empty((world, world), dtype=torch.int64, device=dev)
+        pending = dist.all_gather_into_tensor(matrix, send_n, async_op=True)
+        outgoing = {d: _pack_ghosts(vbg, d, counts[d]) for d in range(world) if d != rank}
+        has_color = next(iter(outgoing.values()))[2]
+        lap("pack")
+        pending.wait()
+        recv_n = matrix[:, rank].cpu().tolist()           # matrix[src][dst] = blocks src sends to dst
+    else:
+        outgoing = {d: _pack_ghosts(vbg, d) for d in range(world) if d != rank}
+        first = next(iter(outgoing.values()))
+        dev, has_color = first[0].device, first[2]
+        send_n = torch.zeros(world, dtype=torch.int64, device=dev)
+        for d, (_, m, _) in outgoing.items():
+            send_n[d] = m
+        matrix = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(matrix, send_n)
+        recv_n = [int(matrix[p][rank]) for p in range(world)]
     total = sum(recv_n[p] for p in range(world) if p != rank)
-    # all incoming payloads land in slices of ONE buffer laid out as a single packed payload of `total`
-    # blocks would need a gather; instead keep per-peer packed buffers and import them together
+    lap("count_matrix")
     incoming, ops = {}, []
     for p in range(world):
         if p == rank:
@@ -111,6 +137,7 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+    lap("p2p")
     if not incoming:
         return 0
     parts = [ghost_views(buf, recv_n[p], has_color) for p, buf in incoming.items()]
@@ -120,6 +147,7 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
         k, t, w = (torch.cat([x[i] for x in parts]) for i in range(3))
         c = torch.cat([x[3] for x in parts]) if has_color else None
     vbg.import_blocks(k, t, w, c)
+    lap("import")
     return total
 
 
@@ -138,23 +166,48 @@ def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangl
     counts = torch.empty((world, 2), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, mine) if dev.type == "cuda" else dist.all_gather(list(counts.unbind(0)), mine)
     counts_h = counts.cpu()
-    vmax, tmax = int(counts_h[:, 0].max()), int(counts_h[:, 1].max())
-
-    def padded(x, n, dtype):
-        out = torch.zeros((n, 3), dtype=dtype, device=dev)
-        if x is not None and x.shape[0]:
-            out[: x.shape[0]] = x
-        return out
-
-    send = [padded(vertices, vmax, torch.float32), padded(normals, vmax, torch.float32),
-            padded(triangles, tmax, torch.int32)]
-    recv = [[torch.empty_like(s) for _ in range(world)] if rank == dst else None for s in send]
-    for s, r in zip(send, recv):
-        dist.gather(s, r, dst=dst)
+    nv, nt = counts_h[:, 0].tolist(), counts_h[:, 1].tolist()
+    # exact-size point-to-point transfers straight into slices of the destination arrays (one NCCL group,
+    # no padding, no concatenation); every rank must agree on whether normals travel
+    has_normals = normals is not None
     if rank != dst:
+        ops = []
+        if nv[rank]:
+            ops.append(dist.P2POp(dist.isend, vertices.contiguous(), dst))
+            if has_normals:
+                ops.append(dist.P2POp(dist.isend, normals.contiguous(), dst))
+        if nt[rank]:
+            ops.append(dist.P2POp(dist.isend, triangles.contiguous(), dst))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
         return None, None, None, counts_h
-    voff = torch.cumsum(counts_h[:, 0], 0) - counts_h[:, 0]
-    v = torch.cat([recv[0][r][: int(counts_h[r, 0])] for r in range(world)])
-    n = torch.cat([recv[1][r][: int(counts_h[r, 0])] for r in range(world)]) if normals is not None else None
-    t = torch.cat([recv[2][r][: int(counts_h[r, 1])] + int(voff[r]) for r in range(world)])
+    voff = [0] * (world + 1)
+    toff = [0] * (world + 1)
+    for r in range(world):
+        voff[r + 1], toff[r + 1] = voff[r] + nv[r], toff[r] + nt[r]
+    v = torch.empty((voff[world], 3), dtype=torch.float32, device=dev)
+    n = torch.empty((voff[world], 3), dtype=torch.float32, device=dev) if has_normals else None
+    t = torch.empty((toff[world], 3), dtype=triangles.dtype, device=dev)
+    ops = []
+    for r in range(world):
+        vs, ts = slice(voff[r], voff[r + 1]), slice(toff[r], toff[r + 1])
+        if r == rank:
+            v[vs] = vertices
+            if has_normals:
+                n[vs] = normals
+            t[ts] = triangles
+            continue
+        if nv[r]:
+            ops.append(dist.P2POp(dist.irecv, v[vs], r))
+            if has_normals:
+                ops.append(dist.P2POp(dist.irecv, n[vs], r))
+        if nt[r]:
+            ops.append(dist.P2POp(dist.irecv, t[ts], r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for r in range(1, world):
+        if nt[r] and voff[r]:
+            t[toff[r]:toff[r + 1]] += voff[r]
     return v, n, t, counts_h

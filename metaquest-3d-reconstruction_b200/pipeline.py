@@ -38,13 +38,34 @@ def pin(a: np.ndarray) -> torch.Tensor:
 def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K, E_wc, params: IntegrationParams,
                      conf: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
                      has_conf: Optional[torch.Tensor] = None, colors_host: Optional[torch.Tensor] = None,
-                     Kc=None) -> SequenceStats:
+                     Kc=None, shard: Optional[tuple] = None) -> SequenceStats:
     """Integrate [F,H,W] raw NDC depth frames (host, ideally pinned) into `vbg`.
 
     conf/count (float64 / int32 [F,H,W], host or device) enable the reference's confidence mask
-    (o3d_utils.py:131-142).  colors_host: uint8 [F,CH,CW,3] enables Open3D's colour overload."""
+    (o3d_utils.py:131-142).  colors_host: uint8 [F,CH,CW,3] enables Open3D's colour overload.
+
+    shard=(rank, world): multi-GPU upload.  Every rank integrates every frame into its own blocks, but each
+    rank moves only 1/world of each chunk over its PCIe link and the chunk is completed by an NCCL
+    all-gather over NVLink (the frame broadcast of SURVEY 8e, sharded), still on the copy stream."""
     dev = vbg.device
     F = int(raw_host.shape[0])
+    if shard is not None and int(shard[1]) > 1:
+        import torch.distributed as dist
+        s_rank, s_world = int(shard[0]), int(shard[1])
+
+        def upload(host, f0, f1):
+            per = -(-(f1 - f0) // s_world)
+            full = torch.empty((per * s_world,) + tuple(host.shape[1:]), dtype=host.dtype, device=dev)
+            a = min(f1, f0 + s_rank * per)
+            b = min(f1, a + per)
+            mine = full[s_rank * per:(s_rank + 1) * per]
+            if b > a:
+                mine[: b - a].copy_(host[a:b], non_blocking=True)
+            dist.all_gather_into_tensor(full, mine)
+            return full[: f1 - f0]
+    else:
+        def upload(host, f0, f1):
+            return host[f0:f1].to(dev, non_blocking=True)
     mask = params.use_confidence_filtered_depth and conf is not None
     use_color = colors_host is not None and vbg.has_color
     chunk = max(1, int(params.batch_frames))
@@ -61,12 +82,12 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     for f0 in range(0, F, chunk):
         f1 = min(F, f0 + chunk)
         with torch.cuda.stream(copy):
-            part = {"raw": raw_host[f0:f1].to(dev, non_blocking=True)}
+            part = {"raw": upload(raw_host, f0, f1)}
             if use_color:
-                part["col"] = colors_host[f0:f1].to(dev, non_blocking=True)
+                part["col"] = upload(colors_host, f0, f1)
             if mask:
-                part["conf"] = conf[f0:f1].to(dev, non_blocking=True)
-                part["count"] = count[f0:f1].to(dev, non_blocking=True)
+                for name, src in (("conf", conf), ("count", count)):
+                    part[name] = upload(src, f0, f1) if src.device.type == "cpu" else src[f0:f1].to(dev)
             ev = torch.cuda.Event()
             ev.record(copy)
         staged.append((f0, f1, part, ev))

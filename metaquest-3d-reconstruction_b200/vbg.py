@@ -174,14 +174,24 @@ class VoxelBlockGrid:
         buf, m, has_color = self.ghost_select_packed(dest_rank)
         return ghost_views(buf, m, has_color)
 
-    def ghost_select_packed(self, dest_rank: int):
+    def ghost_counts(self) -> list:
+        """Number of owned blocks every rank keeps as ghosts ([world] ints; one kernel, one sync)."""
+        world = self.partition[1] if self.partition else 1
+        out = (C.c_int64 * world)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_ghost_counts(self._h, out, _stream()))
+        return [int(x) for x in out]
+
+    def ghost_select_packed(self, dest_rank: int, count: Optional[int] = None):
         """Same selection as one contiguous float32 payload (see ghost_packed_len / ghost_views):
-        (buffer, block count, has_color)."""
+        (buffer, block count, has_color).  With `count` (from ghost_counts) the call is asynchronous."""
         n = C.c_int64()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().mq3d_grid_ghost_select(self._h, int(dest_rank), C.byref(n), None, None, None, None,
-                                                         _stream()))
-            m = int(n.value)
+            if count is None:
+                _lib.check(_lib.lib().mq3d_grid_ghost_select(self._h, int(dest_rank), C.byref(n), None, None, None,
+                                                             None, _stream()))
+                count = int(n.value)
+            m = n.value = int(count)
             buf = torch.empty(ghost_packed_len(m, self.has_color), dtype=torch.float32, device=self.device)
             if m:
                 keys, tsdf, weight, color = ghost_views(buf, m, self.has_color)
@@ -350,8 +360,10 @@ class VoxelBlockGrid:
         return g
 
     # -- K5 -----------------------------------------------------------------------------------------
-    def extract_triangle_mesh_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False):
-        """(vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, vertex_keys i32 [V,4]]) on device."""
+    def extract_triangle_mesh_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False,
+                                     with_colors: bool = False):
+        """(vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, vertex_keys i32 [V,4]][, colors f32
+        [V,3] in 0..1]) on device; colours need the colour attribute."""
         V, T = C.c_int64(), C.c_int64()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mq3d_extract_mesh_count(self._h, C.c_float(weight_threshold), C.byref(V),
@@ -362,9 +374,16 @@ class VoxelBlockGrid:
             vkeys = torch.empty((V.value, 4), dtype=torch.int32, device=self.device) if with_keys else None
             _lib.check(_lib.lib().mq3d_extract_mesh_fill(self._h, _lib.dptr(verts), _lib.dptr(normals),
                                                          _lib.dptr(tris), _lib.dptr(vkeys), _stream()))
-        return (verts, normals, tris, vkeys) if with_keys else (verts, normals, tris)
+            out = (verts, normals, tris) + ((vkeys,) if with_keys else ())
+            if with_colors:
+                cols = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
+                _lib.check(_lib.lib().mq3d_extract_mesh_colors(self._h, _lib.dptr(cols), _stream()))
+                out += (cols,)
+        return out
 
-    def extract_point_cloud_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False):
+    def extract_point_cloud_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False,
+                                   with_colors: bool = False):
+        """(points f32 [P,3], normals f32 [P,3][, point_keys i32 [P,4]][, colors f32 [P,3]]) on device."""
         P = C.c_int64()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mq3d_extract_points_count(self._h, C.c_float(weight_threshold), C.byref(P), _stream()))
@@ -373,17 +392,23 @@ class VoxelBlockGrid:
             pk = torch.empty((P.value, 4), dtype=torch.int32, device=self.device) if with_keys else None
             _lib.check(_lib.lib().mq3d_extract_points_fill(self._h, _lib.dptr(pts), _lib.dptr(nrm), _lib.dptr(pk),
                                                            _stream()))
-        return (pts, nrm, pk) if with_keys else (pts, nrm)
+            out = (pts, nrm) + ((pk,) if with_keys else ())
+            if with_colors:
+                cols = torch.empty((P.value, 3), dtype=torch.float32, device=self.device)
+                _lib.check(_lib.lib().mq3d_extract_points_colors(self._h, _lib.dptr(cols), _stream()))
+                out += (cols,)
+        return out
 
     def extract_triangle_mesh(self, weight_threshold: float = 3.0, estimated_vertex_number: int = -1):
+        """Open3D-shaped result; vertex colours are present when the grid has the colour attribute."""
         from .geometry import TriangleMesh
-        v, n, t = self.extract_triangle_mesh_arrays(weight_threshold)
-        return TriangleMesh(v, t, n)
+        out = self.extract_triangle_mesh_arrays(weight_threshold, with_colors=self.has_color)
+        return TriangleMesh(out[0], out[2], out[1], out[3] if self.has_color else None)
 
     def extract_point_cloud(self, weight_threshold: float = 3.0, estimated_point_number: int = -1):
         from .geometry import PointCloud
-        p, n = self.extract_point_cloud_arrays(weight_threshold)
-        return PointCloud(p, n)
+        out = self.extract_point_cloud_arrays(weight_threshold, with_colors=self.has_color)
+        return PointCloud(out[0], out[1], out[2] if self.has_color else None)
 
 
 def depth_prepare(raw: torch.Tensor, nears, fars, conf: Optional[torch.Tensor] = None,

@@ -162,6 +162,15 @@ class Grid:
         lib().orc_extract_points(self._h, C.c_float(weight_threshold), _p(pts), _p(nrm), _p(pk), C.byref(P))
         return pts, nrm, pk
 
+    def vertex_colors(self, keys: np.ndarray) -> np.ndarray:
+        """Colours (float32 [n,3], 0..1) of mesh vertices / points given their (x,y,z,axis) keys."""
+        keys = np.ascontiguousarray(keys, np.int32)
+        out = np.empty((len(keys), 3), np.float32)
+        rc = lib().orc_vertex_colors(self._h, _p(keys), C.c_int64(len(keys)), _p(out))
+        if rc != 0:
+            raise RuntimeError("orc_vertex_colors: grid has no colour attribute or a key is not allocated")
+        return out
+
 
 def pixel_error_map(K, Ecw, Ecw_inv, ref_idx, ref_depth, tgt_idx, tgt_depth, depth_max):
     K = _f32(K)

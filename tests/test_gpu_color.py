@@ -55,6 +55,39 @@ def test_color_per_frame_matches_oracle(cuda_device, oracle):
     assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
 
 
+def test_mesh_and_point_colors_match_oracle(cuda_device, oracle):
+    """Colour branch of extract_triangle_mesh / extract_point_cloud: bit-exact vs the oracle, matched through the
+    (voxel, axis) keys; also checks the Open3D-shaped objects carry the colours."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    lin, K, Ewc, colors, Kc = _setup(oracle)
+    og = oracle.Grid(0.02, with_color=True)
+    oracle_integrate_sequence(oracle, og, lin, K, Ewc, 4.0, 10.0, colors=colors, Kc=Kc)
+    vbg = VoxelBlockGrid(attr_names=("tsdf", "weight", "color"), voxel_size=0.02, block_count=500, device=cuda_device)
+    vbg.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, 4.0, 10.0,
+                           colors=torch.from_numpy(colors).to(cuda_device), color_intrinsics=Kc)
+    v, n, t, vk, vc = [x.cpu().numpy() for x in vbg.extract_triangle_mesh_arrays(1.5, with_keys=True, with_colors=True)]
+    assert len(v) > 1000 and vc.shape == v.shape
+    ref = og.vertex_colors(vk)
+    assert np.array_equal(ref.view(np.uint32), vc.view(np.uint32))
+    assert 0.0 <= vc.min() and vc.max() <= 1.0 and vc.max() > 0.3
+    # same vertices, oracle order: positions identify the match, colours follow
+    ov, _, _, ovk = og.extract_mesh(1.5)
+    order_o, order_g = np.lexsort(ovk.T[::-1]), np.lexsort(vk.T[::-1])
+    assert np.array_equal(ovk[order_o], vk[order_g])
+    assert np.array_equal(og.vertex_colors(ovk)[order_o].view(np.uint32), vc[order_g].view(np.uint32))
+    p, pn, pk, pc = [x.cpu().numpy() for x in vbg.extract_point_cloud_arrays(1.5, with_keys=True, with_colors=True)]
+    assert len(p) > 1000
+    assert np.array_equal(og.vertex_colors(pk).view(np.uint32), pc.view(np.uint32))
+    mesh = vbg.extract_triangle_mesh(1.5)
+    assert mesh.vertex.colors is not None and tuple(mesh.vertex.colors.shape) == v.shape
+    assert vbg.extract_point_cloud(1.5).point.colors is not None
+    # a colourless grid refuses instead of inventing colours
+    plain = VoxelBlockGrid(voxel_size=0.02, block_count=500, device=cuda_device)
+    plain.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, 4.0, 10.0)
+    with pytest.raises(Exception):
+        plain.extract_triangle_mesh_arrays(1.5, with_colors=True)
+
+
 def test_depth_scale_is_applied(cuda_device, oracle):
     """depth_scale != 1 (never used by the reference, supported by Open3D): depth / scale per sample."""
     from mq3d_b200.vbg import VoxelBlockGrid

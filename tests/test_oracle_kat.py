@@ -110,6 +110,30 @@ def test_mc_plane(oracle):
     assert (nz > 0).all() or (nz < 0).all()
 
 
+def test_mc_plane_colors(oracle):
+    """Colour branch: a colour ramp along z is interpolated at the crossing with the vertex's own ratio and
+    scaled by 1/255."""
+    c = 20.4
+    g0, keys = _plane_grid(oracle, c)
+    k, t, w, _ = g0.export()
+    zz = np.arange(16, dtype=np.float32)[:, None, None] * np.ones((16, 16, 16), np.float32)
+    col = np.zeros(t.shape + (3,), np.float32)
+    for i, key in enumerate(k):
+        col[i, ..., 0] = 10.0 * (key[2] * 16 + zz)
+        col[i, ..., 2] = 255.0
+    g = oracle.Grid(VS, with_color=True)
+    g.load(k, t, w, col)
+    v, n, tr, vk = g.extract_mesh(3.0)
+    vc = g.vertex_colors(vk)
+    assert vc.shape == v.shape
+    assert np.allclose(vc[:, 0], (0.6 * 200.0 + 0.4 * 210.0) / 255.0, atol=1e-5)
+    assert np.array_equal(vc[:, 1], np.zeros(len(vc), np.float32)) and np.allclose(vc[:, 2], 1.0, atol=1e-6)
+    p, pn, pk = g.extract_points(3.0)
+    assert np.allclose(g.vertex_colors(pk)[:, 0], 204.0 / 255.0, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        g0.vertex_colors(vk)                      # colourless grid
+
+
 def test_mc_weight_threshold_is_strict(oracle):
     g, _ = _plane_grid(oracle, 20.4, w=3.0)
     assert len(g.extract_mesh(3.0)[0]) == 0          # w == threshold is rejected (w <= thr)
