@@ -228,9 +228,8 @@ def run_gpu(args):
     if os.environ.get("MQ3D_TRACE"):
         print("[bench] per-step mc ms:", [round(x, 3) for x in mc_list], file=sys.stderr)
         if xch_phases:
-            calls = args.steps + args.warmup
-            print(f"[bench r{rank}] exchange phases ms/step:", {k: round(v / calls, 3) for k, v in xch_phases.items()},
-                  file=sys.stderr)
+            print(f"[bench r{rank}] exchange phases, median ms/step:",
+                  {k: round(float(np.median(v)), 3) for k, v in xch_phases.items()}, file=sys.stderr)
     mc_ms = float(np.mean(mc_list))
     st = stats[-1]
     integ_ms = float(np.mean([s.integrate_ms for s in stats]))

@@ -215,24 +215,38 @@ extern "C" int mq3d_scene_add_triangles(mq3d_scene *s, const float *vertices_dev
     MQ3D_REQUIRE(vertices_dev && triangles_dev, "null geometry");
     cudaStream_t st = as_stream(stream);
     const int n = (int)n_triangles;
+    // one scratch arena for the build (a single allocation / free instead of ten)
     unsigned *bounds = nullptr;
     unsigned long long *keys = nullptr, *keys_sorted = nullptr;
     float *leaf_box = nullptr, *node_box = nullptr;
     int *left = nullptr, *right = nullptr, *parent = nullptr, *flags = nullptr;
     void *tmp = nullptr;
+    char *arena = nullptr;
     size_t tmp_bytes = 0;
     int rc = [&]() -> int {
-        MQ3D_CUDA(cudaMalloc(&bounds, sizeof(unsigned) * 6));
-        MQ3D_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * n));
-        MQ3D_CUDA(cudaMalloc(&keys_sorted, sizeof(unsigned long long) * n));
-        MQ3D_CUDA(cudaMalloc(&leaf_box, sizeof(float) * 6 * n));
-        MQ3D_CUDA(cudaMalloc(&node_box, sizeof(float) * 6 * (n > 1 ? n - 1 : 1)));
-        MQ3D_CUDA(cudaMalloc(&left, sizeof(int) * n));
-        MQ3D_CUDA(cudaMalloc(&right, sizeof(int) * n));
-        MQ3D_CUDA(cudaMalloc(&parent, sizeof(int) * 2 * n));
-        MQ3D_CUDA(cudaMalloc(&flags, sizeof(int) * n));
+        MQ3D_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys_sorted, n, 0, 64, st));
+        const size_t nn = (size_t)n, ni = (size_t)(n > 1 ? n - 1 : 1);
+        const size_t sizes[10] = {sizeof(unsigned) * 6, sizeof(unsigned long long) * nn, sizeof(unsigned long long) * nn,
+                                  sizeof(float) * 6 * nn, sizeof(float) * 6 * ni, sizeof(int) * nn, sizeof(int) * nn,
+                                  sizeof(int) * 2 * nn, sizeof(int) * nn, tmp_bytes};
+        size_t offs[10], total = 0;
+        for (int i = 0; i < 10; ++i) {
+            offs[i] = total;
+            total += (sizes[i] + 255) & ~(size_t)255;
+        }
+        MQ3D_CUDA(cudaMalloc(&arena, total));
+        bounds = reinterpret_cast<unsigned *>(arena + offs[0]);
+        keys = reinterpret_cast<unsigned long long *>(arena + offs[1]);
+        keys_sorted = reinterpret_cast<unsigned long long *>(arena + offs[2]);
+        leaf_box = reinterpret_cast<float *>(arena + offs[3]);
+        node_box = reinterpret_cast<float *>(arena + offs[4]);
+        left = reinterpret_cast<int *>(arena + offs[5]);
+        right = reinterpret_cast<int *>(arena + offs[6]);
+        parent = reinterpret_cast<int *>(arena + offs[7]);
+        flags = reinterpret_cast<int *>(arena + offs[8]);
+        tmp = arena + offs[9];
         MQ3D_CUDA(cudaMalloc(&s->tri, sizeof(float4) * 3 * n));
-        MQ3D_CUDA(cudaMalloc(&s->nodes, sizeof(BvhNode) * (n > 1 ? n - 1 : 1)));
+        MQ3D_CUDA(cudaMalloc(&s->nodes, sizeof(BvhNode) * ni));
         unsigned init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
         MQ3D_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
         MQ3D_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * n, st));
@@ -241,8 +255,6 @@ extern "C" int mq3d_scene_add_triangles(mq3d_scene *s, const float *vertices_dev
         k_scene_bounds<<<grid, 256, 0, st>>>(vertices_dev, triangles_dev, n, bounds);
         k_morton<<<grid, 256, 0, st>>>(vertices_dev, triangles_dev, n, bounds, keys);
         MQ3D_CUDA(cudaGetLastError());
-        MQ3D_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys_sorted, n, 0, 64, st));
-        MQ3D_CUDA(cudaMalloc(&tmp, tmp_bytes));
         MQ3D_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys_sorted, n, 0, 64, st));
         k_gather_tris<<<grid, 256, 0, st>>>(vertices_dev, triangles_dev, keys_sorted, n, s->tri, leaf_box);
         if (n > 1) {
@@ -253,8 +265,7 @@ extern "C" int mq3d_scene_add_triangles(mq3d_scene *s, const float *vertices_dev
         MQ3D_CUDA(cudaStreamSynchronize(st));
         return MQ3D_OK;
     }();
-    cudaFree(bounds); cudaFree(keys); cudaFree(keys_sorted); cudaFree(leaf_box); cudaFree(node_box);
-    cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(flags); cudaFree(tmp);
+    cudaFree(arena);
     if (rc != MQ3D_OK) return rc;
     s->n_tris = n;
     return MQ3D_OK;

@@ -95,7 +95,7 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
             now = _time.perf_counter()
-            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            timings.setdefault(name, []).append((now - t_last[0]) * 1e3)
             t_last[0] = now
 
     if hasattr(vbg, "ghost_counts"):

@@ -91,11 +91,14 @@ def main():
     vbg.integrate_sequence(lin2, K2, Ewc2, 4.0, 10.0, frame_valid=valid2)
     mesh = vbg.extract_triangle_mesh(1.5)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    scene = RaycastingScene(device=dev)
-    scene.add_triangles(mesh)
-    torch.cuda.synchronize()
-    build_ms = (time.perf_counter() - t0) * 1e3
+    builds = []
+    for _ in range(4):          # first build pays module load + first-touch allocations
+        t0 = time.perf_counter()
+        scene = RaycastingScene(device=dev)
+        scene.add_triangles(mesh)
+        torch.cuda.synchronize()
+        builds.append((time.perf_counter() - t0) * 1e3)
+    build_ms = min(builds)
     Kc = np.array([[870.0, 0, 640.0], [0, 870.0, 480.0], [0, 0, 1.0]], np.float32)
     views = list(range(0, F2, max(1, F2 // args.views)))[: args.views]
 
@@ -108,7 +111,7 @@ def main():
     ms, t_hit = timed(render, 3, 1)
     nrays = len(views) * 1280 * 960
     line = {"kernel": "k_cast_rays(+k_rays_pinhole)", "triangles": int(mesh.triangle.indices.shape[0]),
-            "views": len(views), "ms_per_view": ms / len(views), "mrays_per_s": nrays / ms * 1e-3, "bvh_build_ms": build_ms,
+            "views": len(views), "ms_per_view": ms / len(views), "mrays_per_s": nrays / ms * 1e-3, "bvh_build_ms": build_ms, "bvh_build_ms_first_call": builds[0],
             "hit_fraction_last_view": float(torch.isfinite(t_hit).float().mean())}
     if args.cpu:
         from oracle import oracle as orc
