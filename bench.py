@@ -188,6 +188,10 @@ def run_gpu(args):
             from mq3d_b200.dist import exchange_ghosts
             exchange_ghosts(vbg, rank, world, timings=xch_phases)   # owners -> ghost shells, once, before extraction
             torch.cuda.synchronize()
+        elif world > 1 and args.ghosts == "pull":
+            from mq3d_b200.dist import pull_ghosts
+            pull_ghosts(vbg, rank, world)            # ghost shells read straight from the owners' pools (NVLink)
+            torch.cuda.synchronize()
         t_b = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -253,6 +257,9 @@ def run_gpu(args):
                          Kc=wl["Kc"], shard=(rank, world))
         if args.ghosts == "exchange":
             exchange_ghosts(vbg, rank, world)
+        elif args.ghosts == "pull":
+            from mq3d_b200.dist import pull_ghosts
+            pull_ghosts(vbg, rank, world)
         v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
         gv, gn, gt, _ = gather_mesh(v, nrm, t, dst=0)
         if rank != 0:
@@ -434,7 +441,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames per side")
     ap.add_argument("--batch", type=int, default=64, help="frames per block residency (<= 256)")
     ap.add_argument("--tile", type=int, default=4, help="partition super-tile edge in blocks (N > 1)")
-    ap.add_argument("--ghosts", default="exchange", choices=["exchange", "integrate"],
+    ap.add_argument("--ghosts", default="exchange", choices=["exchange", "pull", "integrate"],
                     help="N > 1: 'integrate' = every rank also integrates its ghost shell (no exchange, the "
                          "north-star scheme); 'exchange' = owned blocks only + one ghost-block exchange before MC")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded CPU sample")

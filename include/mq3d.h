@@ -90,6 +90,18 @@ int mq3d_grid_ghost_select(mq3d_grid *g, int dest_rank, int64_t *n_out, int32_t 
  * own rank is 0).  Passing a count obtained here as *n_out to mq3d_grid_ghost_select (with buffers) makes
  * that call fully asynchronous: no host synchronisation, payload valid in stream order. */
 int mq3d_grid_ghost_counts(mq3d_grid *g, int64_t *counts_out, void *stream);
+/* Ghost shell by peer memory (CUDA IPC over NVLink / NVSwitch), the alternative to select + send/recv +
+ * import: every rank publishes a MQ3D_PEER_DESC_BYTES descriptor of its pool (IPC handles, block count),
+ * the host all-gathers the descriptors (stream-ordered after integration, so the collective is also the
+ * "all ranks finished integrating" barrier) and calls mq3d_grid_ghost_pull with the [world] array: one
+ * kernel lists the peers' owned blocks inside this rank's shell straight from the peers' key arrays,
+ * another copies tsdf | weight | colour from the owners' pools into the local pool.  The caller must
+ * fence (any stream-ordered collective) before any rank changes its grid again.  Pools exported this
+ * way are retired instead of freed on growth, until the grid is destroyed.  Grids living in the same
+ * process (rank-by-rank emulation) are read through their plain device pointers. */
+#define MQ3D_PEER_DESC_BYTES 512
+int mq3d_grid_peer_descriptor(mq3d_grid *g, void *desc_out, void *stream);
+int mq3d_grid_ghost_pull(mq3d_grid *g, const void *descs, int64_t *n_pulled, void *stream);
 
 /* ---- K1: raw NDC depth -> linear metres + confidence mask -----------------------------------
  * Replaces DepthDataIO.load_depth_map's convert_depth_to_linear + is_depth_map_valid

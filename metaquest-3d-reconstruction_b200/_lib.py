@@ -26,7 +26,7 @@ SYMBOLS = [
     "mq3d_grid_create", "mq3d_grid_destroy", "mq3d_grid_reset", "mq3d_grid_reserve",
     "mq3d_grid_num_blocks", "mq3d_grid_info", "mq3d_grid_pool", "mq3d_grid_export", "mq3d_grid_import",
     "mq3d_grid_set_partition", "mq3d_grid_set_ghost_mode", "mq3d_grid_ghost_select",
-    "mq3d_grid_ghost_counts",
+    "mq3d_grid_ghost_counts", "mq3d_grid_peer_descriptor", "mq3d_grid_ghost_pull",
     "mq3d_depth_prepare", "mq3d_touch", "mq3d_integrate", "mq3d_integrate_sequence",
     "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_points_count",
     "mq3d_extract_points_fill", "mq3d_extract_mesh_colors", "mq3d_extract_points_colors", "mq3d_confidence",
@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         "mq3d_grid_set_ghost_mode": [vp, i32],
         "mq3d_grid_ghost_select": [vp, i32, C.POINTER(i64), vp, vp, vp, vp, vp],
         "mq3d_grid_ghost_counts": [vp, C.POINTER(i64), vp],
+        "mq3d_grid_peer_descriptor": [vp, vp, vp],
+        "mq3d_grid_ghost_pull": [vp, vp, C.POINTER(i64), vp],
         "mq3d_depth_prepare": [vp, i32, i32, i32, pd, pd, vp, vp, vp, f64, C.c_int32, vp, vp, vp],
         "mq3d_touch": [vp, vp, i32, i32, pd, pd, f32, f32, f32, vp, C.POINTER(i64), vp],
         "mq3d_integrate": [vp, vp, i64, vp, i32, i32, vp, i32, i32, pd, pd, pd, f32, f32, f32, vp],

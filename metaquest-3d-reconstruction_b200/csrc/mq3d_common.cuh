@@ -223,6 +223,12 @@ struct mq3d_grid {
     int32_t *idx_scratch;  // per-frame integrate: block index per key
     int64_t idx_scratch_size;
     int *ghost_cnt_dev, *ghost_cnt_host;  // [64] per-destination ghost counts (device / pinned)
+    // peer-memory ghost pull (mq3d_peer.cu): once a pool has been exported to other processes its
+    // allocations are retired instead of freed on growth (peers may still have them mapped)
+    int ipc_exported;
+    void **retired;
+    int n_retired, cap_retired;
+    struct mq3d_peer_state *peer;
     int *pinned_host;    // pinned int[8] for async readbacks
     int64_t *pinned_host64;            // two pinned int64 (tail of pinned_host) for the MC totals
     int *frame_counts_dev;             // [MQ3D_MAX_BATCH]
@@ -248,3 +254,4 @@ int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool 
 int mq3d_set_device(int device);
 // Activate + Find for an explicit key list; block indices land in g->idx_scratch.
 int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st);
+void mq3d_peer_state_free(mq3d_grid *g);   // mq3d_peer.cu

@@ -88,9 +88,26 @@ static int alloc_slot_scratch(mq3d_grid *g, cudaStream_t st) {
     return MQ3D_OK;
 }
 
+// free a pool array -- or park it until destroy when other processes may still have it mapped
+static void release_pool_ptr(mq3d_grid *g, void *p) {
+    if (!p) return;
+    if (!g->ipc_exported) {
+        cudaFree(p);
+        return;
+    }
+    if (g->n_retired == g->cap_retired) {
+        g->cap_retired = g->cap_retired ? 2 * g->cap_retired : 16;
+        g->retired = (void **)realloc(g->retired, sizeof(void *) * g->cap_retired);
+    }
+    g->retired[g->n_retired++] = p;
+}
+
 static int alloc_pool(mq3d_grid *g, int64_t cap, int32_t **keys, float **tsdf, float **weight, float **color,
                       cudaStream_t st) {
-    MQ3D_CUDA(cudaMalloc(keys, sizeof(int32_t) * 3 * cap));
+    // at least one 2 MB page so the key array never shares a driver block with other small allocations
+    // (its IPC handle is exported by mq3d_grid_peer_descriptor)
+    size_t key_bytes = sizeof(int32_t) * 3 * (size_t)cap;
+    MQ3D_CUDA(cudaMalloc(keys, key_bytes < ((size_t)2 << 20) ? ((size_t)2 << 20) : key_bytes));
     MQ3D_CUDA(cudaMalloc(tsdf, sizeof(float) * MQ3D_RES3 * cap));
     MQ3D_CUDA(cudaMalloc(weight, sizeof(float) * MQ3D_RES3 * cap));
     *color = nullptr;
@@ -197,6 +214,9 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->frame_params_dev);
     cudaFree(g->idx_scratch);
     cudaFree(g->ghost_cnt_dev);
+    mq3d_peer_state_free(g);
+    for (int q = 0; q < g->n_retired; ++q) cudaFree(g->retired[q]);
+    free(g->retired);
     if (g->ghost_cnt_host) cudaFreeHost(g->ghost_cnt_host);
     if (g->pinned_host) cudaFreeHost(g->pinned_host);
     cudaFree(g->frame_counts_dev);
@@ -403,10 +423,10 @@ int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool 
             MQ3D_CUDA(cudaMemsetAsync(nc + 3 * MQ3D_RES3 * live, 0, sizeof(float) * 3 * MQ3D_RES3 * (new_cap - live), st));
         }
         MQ3D_CUDA(cudaStreamSynchronize(st));
-        cudaFree(g->block_keys);
-        cudaFree(g->tsdf);
-        cudaFree(g->weight);
-        cudaFree(g->color);
+        release_pool_ptr(g, g->block_keys);
+        release_pool_ptr(g, g->tsdf);
+        release_pool_ptr(g, g->weight);
+        release_pool_ptr(g, g->color);
         g->block_keys = nk;
         g->tsdf = nt;
         g->weight = nw;

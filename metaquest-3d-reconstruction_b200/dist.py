@@ -151,6 +151,39 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
     return total
 
 
+def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fence: bool = True) -> int:
+    """Owned-only integration mode, peer-memory variant of exchange_ghosts: all-gather the 512-byte pool
+    descriptors (CUDA IPC handles; the collective is stream-ordered after integration, so it is also the
+    "everyone has finished integrating" barrier), then each rank copies the blocks of its ghost shell straight
+    out of the owners' pools over NVLink (vbg.ghost_pull: two kernels, no staging, no send/recv, no import).
+    fence=True enqueues a tiny all-reduce afterwards so that no rank's later work (grid reset, next
+    integration) can overtake a peer that is still reading its pool; nothing waits on the host for it.
+    Returns the number of ghost blocks fetched."""
+    import torch.distributed as dist
+    if rank is None:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return 0
+    dev = torch.device(vbg.device)
+    mine = torch.from_numpy(vbg.peer_descriptor()).to(dev, non_blocking=True)
+    table = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(table, mine)
+    n = vbg.ghost_pull(table.cpu().numpy())
+    if fence:
+        dist.all_reduce(_fence_token(dev))
+    return n
+
+
+_FENCE: dict = {}
+
+
+def _fence_token(dev: torch.device) -> torch.Tensor:
+    key = (dev.type, dev.index)
+    if key not in _FENCE:
+        _FENCE[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return _FENCE[key]
+
+
 def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangles: torch.Tensor, dst: int = 0):
     """Concatenate per-rank meshes on `dst`: vertex arrays are appended in rank order and triangle
     indices rebased by the exclusive scan of the per-rank vertex counts.  Returns (vertices, normals,

@@ -17,6 +17,7 @@ import torch
 from . import _lib
 
 RES = 16
+PEER_DESC_BYTES = 512      # MQ3D_PEER_DESC_BYTES
 
 
 def _stream():
@@ -181,6 +182,26 @@ class VoxelBlockGrid:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mq3d_grid_ghost_counts(self._h, out, _stream()))
         return [int(x) for x in out]
+
+    def peer_descriptor(self) -> np.ndarray:
+        """uint8 [512] description of this rank's pool (CUDA IPC handles + block count) for ghost_pull."""
+        desc = np.zeros(PEER_DESC_BYTES, np.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_peer_descriptor(self._h, desc.ctypes.data_as(C.c_void_p), _stream()))
+        return desc
+
+    def ghost_pull(self, descs: np.ndarray) -> int:
+        """Fetch the ghost shell straight from the owners' pools (peer memory over NVLink).  descs: uint8
+        [world, 512], row r = rank r's peer_descriptor().  Asynchronous on the current stream apart from one
+        count readback; the caller fences (stream-ordered collective) before any grid changes again."""
+        descs = np.ascontiguousarray(descs, np.uint8)
+        world = self.partition[1] if self.partition else 1
+        if descs.shape != (world, PEER_DESC_BYTES):
+            raise RuntimeError(f"descs must be uint8 [{world}, {PEER_DESC_BYTES}]")
+        n = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mq3d_grid_ghost_pull(self._h, descs.ctypes.data_as(C.c_void_p), C.byref(n), _stream()))
+        return int(n.value)
 
     def ghost_select_packed(self, dest_rank: int, count: Optional[int] = None):
         """Same selection as one contiguous float32 payload (see ghost_packed_len / ghost_views):

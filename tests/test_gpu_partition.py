@@ -129,3 +129,53 @@ def test_owned_only_integration_plus_ghost_exchange(cuda_device, oracle, world, 
         assert not (tk & union_tris)
         union_tris |= tk
     assert union_tris == full_tris
+
+
+@pytest.mark.parametrize("world,tile,color", [(2, 2, False), (3, 4, True)])
+def test_ghost_pull_from_peer_pools(cuda_device, oracle, world, tile, color):
+    """Peer-memory ghost fetch (mq3d_grid_peer_descriptor + mq3d_grid_ghost_pull), emulated rank by rank in one
+    process (descriptors then carry plain device pointers): afterwards every rank holds exactly the blocks --
+    and bit-exactly the values -- of the single grid inside its shell; the small initial capacity forces pool
+    growth during the pull, i.e. the exported pools are retired, not freed, while peers still read them."""
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    from mq3d_b200.dist import block_needed
+    from mq3d_b200.vbg import VoxelBlockGrid
+    cap = capture(8)
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = torch.from_numpy(np.stack([oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i])
+                                     for i in range(len(ds))])).to(cuda_device)
+    attrs = ("tsdf", "weight", "color") if color else ("tsdf", "weight")
+    kw = {}
+    if color:
+        f, cw, ch = 110.0, 160, 120
+        cols = np.stack([synth.make_color_frame(Ecw[i], width=cw, height=ch, f=f) for i in range(len(ds))])
+        kw = dict(colors=torch.from_numpy(cols).to(cuda_device),
+                  color_intrinsics=np.tile(np.array([[f, 0, cw / 2.0], [0, f, ch / 2.0], [0, 0, 1.0]]), (len(ds), 1, 1)))
+    full = VoxelBlockGrid(attr_names=attrs, voxel_size=0.02, block_count=2000, device=cuda_device)
+    full.integrate_sequence(lin, K, Ewc, 4.0, 10.0, **kw)
+    exp = [x.cpu().numpy() if x is not None else None for x in full.export_blocks()]
+    ref = {tuple(k): i for i, k in enumerate(exp[0].tolist())}
+    grids = []
+    for rank in range(world):
+        g = VoxelBlockGrid(attr_names=attrs, voxel_size=0.02, block_count=64, device=cuda_device)
+        g.set_partition(rank, world, tile, integrate_ghosts=False)
+        g.integrate_sequence(lin, K, Ewc, 4.0, 10.0, **kw)
+        grids.append(g)                    # capacity grew x2 from 64: the pull outgrows it on some ranks
+    descs = np.stack([g.peer_descriptor() for g in grids])
+    assert descs.shape == (world, 512)
+    pulled = [g.ghost_pull(descs) for g in grids]
+    torch.cuda.synchronize()
+    assert sum(pulled) > 0
+    for rank, g in enumerate(grids):
+        got = [x.cpu().numpy() if x is not None else None for x in g.export_blocks()]
+        assert {tuple(x) for x in got[0].tolist()} == {key for key in ref if block_needed(*key, rank, world, tile)}
+        for i, key in enumerate(got[0].tolist()):
+            j = ref[tuple(key)]
+            assert np.array_equal(got[1][i].view(np.uint32), exp[1][j].view(np.uint32))
+            assert np.array_equal(got[2][i], exp[2][j])
+            if color:
+                assert np.array_equal(got[3][i].view(np.uint32), exp[3][j].view(np.uint32))
+    with pytest.raises(Exception):
+        grids[0].ghost_pull(descs[::-1].copy())          # descriptors out of rank order are rejected
