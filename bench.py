@@ -189,8 +189,10 @@ def run_gpu(args):
             exchange_ghosts(vbg, rank, world, timings=xch_phases)   # owners -> ghost shells, once, before extraction
             torch.cuda.synchronize()
         elif world > 1 and args.ghosts == "pull":
-            from mq3d_b200.dist import pull_ghosts
-            pull_ghosts(vbg, rank, world)            # ghost shells read straight from the owners' pools (NVLink)
+            from mq3d_b200.dist import fill_ghost_shell
+            # ghost shells read straight from the owners' pools (NVLink peer memory); falls back to the NCCL
+            # exchange on all ranks if CUDA IPC is unavailable
+            ghost_mode_used[0] = fill_ghost_shell(vbg, rank, world, "pull")
             torch.cuda.synchronize()
         t_b = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -207,6 +209,7 @@ def run_gpu(args):
         return st, (v, nrm, t), (e0, e1)
 
     mgpu_ms = {"exchange": [], "gather": []}
+    ghost_mode_used = [args.ghosts]
     xch_phases = {} if os.environ.get("MQ3D_TRACE") else None      # per-phase exchange times (diagnostics)
 
     # ---- device-resident timing -------------------------------------------------------------------
@@ -258,8 +261,8 @@ def run_gpu(args):
         if args.ghosts == "exchange":
             exchange_ghosts(vbg, rank, world)
         elif args.ghosts == "pull":
-            from mq3d_b200.dist import pull_ghosts
-            pull_ghosts(vbg, rank, world)
+            from mq3d_b200.dist import fill_ghost_shell
+            fill_ghost_shell(vbg, rank, world, "pull")
         v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
         gv, gn, gt, _ = gather_mesh(v, nrm, t, dst=0)
         if rank != 0:
@@ -321,7 +324,7 @@ def run_gpu(args):
                    "color": "1280x960 u8 RGB" if color else None, "voxel_size": cfg["voxel"], "block": "16^3",
                    "trunc_voxel_multiplier": cfg["trunc"], "depth_max": cfg["depth_max"],
                    "weight_threshold": cfg["weight_thr"], "batch_frames": args.batch,
-                   "partition": f"tile-hash T={args.tile}, ghost shell by {args.ghosts}" if world > 1 else "single GPU",
+                   "partition": f"tile-hash T={args.tile}, ghost shell by {ghost_mode_used[0]}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (depth+RGB sequence > 126 MB); no explicit flush"},
         "gvoxel_updates_per_s": visits / (ms_per_step * 1e-3) / 1e9,
         "gvoxel_visits_per_s_integrate_kernel": visits / (integ_ms * 1e-3) / 1e9,
@@ -440,10 +443,12 @@ def main():
     ap.add_argument("--workload", default="quest300_rgb_v10mm", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames per side")
     ap.add_argument("--batch", type=int, default=64, help="frames per block residency (<= 256)")
-    ap.add_argument("--tile", type=int, default=4, help="partition super-tile edge in blocks (N > 1)")
-    ap.add_argument("--ghosts", default="exchange", choices=["exchange", "pull", "integrate"],
+    ap.add_argument("--tile", type=int, default=1, help="partition super-tile edge in blocks (N > 1)")
+    ap.add_argument("--ghosts", default="pull", choices=["pull", "exchange", "integrate"],
                     help="N > 1: 'integrate' = every rank also integrates its ghost shell (no exchange, the "
-                         "north-star scheme); 'exchange' = owned blocks only + one ghost-block exchange before MC")
+                         "north-star scheme); 'exchange' = owned blocks only + one packed NCCL ghost-block "
+                         "exchange before MC; 'pull' = owned blocks only + ghost blocks copied straight from the "
+                         "owners' pools over NVLink peer memory (falls back to 'exchange' without CUDA IPC)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,8 +1,11 @@
 """Multi-GPU plumbing: voxel blocks are partitioned by a spatial hash of their super-tile,
-every rank integrates the broadcast frames into the blocks it owns plus a one-block ghost shell
-(values are bit-identical to the owner's, so there is no halo exchange), meshes are extracted per
-rank for owned cubes only and gathered on rank 0.  torch.distributed (NCCL on the box, gloo in the
-CPU tests) carries exactly two things: the frame broadcast and this final gather.
+every rank sees every frame and integrates the blocks it owns; the one-block ghost shell marching cubes
+needs is either integrated redundantly (no communication), exchanged as packed blocks over NCCL
+(exchange_ghosts) or -- the default -- read straight out of the owners' pools through CUDA-IPC peer
+memory over NVLink (pull_ghosts / fill_ghost_shell); all three give bit-identical grids.  Meshes are
+extracted per rank for owned cubes only and gathered on rank 0 (gather_mesh).  torch.distributed (NCCL
+on the box, gloo in the CPU tests) carries the frame broadcast / sharded upload all-gather, the
+512-byte pool descriptors and the final gather.
 
 The Python functions below restate the device-side ownership rule (csrc/mq3d_common.cuh:
 mq3d_tile_owner / mq3d_block_needed) so that tests can check the partition without a GPU.
@@ -156,22 +159,60 @@ def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fe
     descriptors (CUDA IPC handles; the collective is stream-ordered after integration, so it is also the
     "everyone has finished integrating" barrier), then each rank copies the blocks of its ghost shell straight
     out of the owners' pools over NVLink (vbg.ghost_pull: two kernels, no staging, no send/recv, no import).
-    fence=True enqueues a tiny all-reduce afterwards so that no rank's later work (grid reset, next
-    integration) can overtake a peer that is still reading its pool; nothing waits on the host for it.
-    Returns the number of ghost blocks fetched."""
+    A tiny all-reduce afterwards keeps any rank's later work (grid reset, next integration) from overtaking
+    a peer that is still reading its pool and carries the per-rank status; with fence=True (default) the
+    host reads it, so a failure anywhere raises PeerPullError everywhere (the grids are still valid for
+    exchange_ghosts).  Returns the number of ghost blocks fetched."""
     import torch.distributed as dist
     if rank is None:
         rank, world = dist.get_rank(), dist.get_world_size()
     if world == 1:
         return 0
     dev = torch.device(vbg.device)
-    mine = torch.from_numpy(vbg.peer_descriptor()).to(dev, non_blocking=True)
+    ok, err, n = 1, None, 0
+    try:
+        mine = torch.from_numpy(vbg.peer_descriptor()).to(dev, non_blocking=True)
+    except Exception as e:                      # e.g. CUDA IPC not permitted in this container
+        ok, err = 0, e
+        mine = torch.zeros(PEER_DESC_BYTES, dtype=torch.uint8, device=dev)
     table = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(table, mine)
-    n = vbg.ghost_pull(table.cpu().numpy())
-    if fence:
-        dist.all_reduce(_fence_token(dev))
+    if ok:
+        try:
+            n = vbg.ghost_pull(table.cpu().numpy())
+        except Exception as e:
+            ok, err = 0, e
+    # the fence doubles as the status exchange: every rank learns whether every pull was issued
+    tok = _fence_token(dev)
+    tok.fill_(ok)
+    dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+    if fence or not ok:
+        if int(tok.item()) == 0:
+            raise PeerPullError(f"peer-memory ghost pull failed on some rank (this rank: {err})")
     return n
+
+
+class PeerPullError(RuntimeError):
+    """Raised on EVERY rank when the peer-memory pull could not be issued on some rank."""
+
+
+PEER_DESC_BYTES = 512
+_PULL_USABLE = [True]
+
+
+def fill_ghost_shell(vbg, rank: Optional[int] = None, world: Optional[int] = None, mode: str = "pull") -> str:
+    """Owned-only integration mode: fetch the ghost shell before extraction.  mode "pull" uses peer memory
+    (pull_ghosts) and falls back -- consistently on all ranks, for the rest of the process -- to the packed
+    NCCL exchange (exchange_ghosts) if CUDA IPC is unavailable; mode "exchange" forces the latter.  Returns
+    the mode that was used."""
+    if mode == "pull" and _PULL_USABLE[0]:
+        try:
+            pull_ghosts(vbg, rank, world)
+            return "pull"
+        except PeerPullError:
+            _PULL_USABLE[0] = False
+    exchange_ghosts(vbg, rank, world)
+    return "exchange"
 
 
 _FENCE: dict = {}
