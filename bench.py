@@ -197,16 +197,18 @@ def run_gpu(args):
         t_b = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
+        # Open3D's extract_triangle_mesh on a coloured grid also yields vertex colours
+        out = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"], with_colors=color)
+        v, nrm, t, vc = out[0], out[1], out[2], (out[3] if color else None)
         e1.record()
         t_c = time.perf_counter()
         if world > 1:            # the north star's "final gather": per-rank meshes -> rank 0 over NCCL
             from mq3d_b200.dist import gather_mesh
-            gather_mesh(v, nrm, t, dst=0)
+            gather_mesh(v, nrm, t, dst=0, colors=vc)
             torch.cuda.synchronize()
         mgpu_ms["exchange"].append((t_b - t_a) * 1e3)
         mgpu_ms["gather"].append((time.perf_counter() - t_c) * 1e3)
-        return st, (v, nrm, t), (e0, e1)
+        return st, (v, nrm, t, vc), (e0, e1)
 
     mgpu_ms = {"exchange": [], "gather": []}
     ghost_mode_used = [args.ghosts]
@@ -252,7 +254,7 @@ def run_gpu(args):
         if world == 1:
             integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params, colors_host=col_host,
                              Kc=wl["Kc"])
-            return extract_mesh_to_host(vbg, cfg["weight_thr"])
+            return extract_mesh_to_host(vbg, cfg["weight_thr"], with_colors=color)
         # N > 1: every rank uploads 1/N of each chunk over its own PCIe link, NCCL all-gather completes the
         # chunk over NVLink; per-rank meshes are gathered on rank 0, which reads the whole mesh back
         from mq3d_b200.dist import exchange_ghosts, gather_mesh
@@ -263,12 +265,13 @@ def run_gpu(args):
         elif args.ghosts == "pull":
             from mq3d_b200.dist import fill_ghost_shell
             fill_ghost_shell(vbg, rank, world, "pull")
-        v, nrm, t = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
-        gv, gn, gt, _ = gather_mesh(v, nrm, t, dst=0)
+        out = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"], with_colors=color)
+        got = gather_mesh(out[0], out[1], out[2], dst=0, colors=out[3] if color else None)
         if rank != 0:
             torch.cuda.synchronize()
-            return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)
-        return gv.cpu().numpy(), gn.cpu().numpy(), gt.cpu().numpy()
+            return (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+        host = (got[0].cpu().numpy(), got[1].cpu().numpy(), got[2].cpu().numpy())
+        return host + ((got[4].cpu().numpy(),) if color else ())
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -277,12 +280,13 @@ def run_gpu(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
-        hv, hn, ht = step_e2e()
+        host_mesh = step_e2e()
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
     h2d = raw_host.numel() * 4 + (col_host.numel() if color else 0)
-    d2h = hv.nbytes + hn.nbytes + ht.nbytes
+    hv, ht = host_mesh[0], host_mesh[2]
+    d2h = sum(a.nbytes for a in host_mesh)
 
     # ---- reduce over ranks (max time; sums of per-rank work) --------------------------------------
     t = torch.tensor([total_ms, e2e_ms, integ_ms, touch_ms, mc_ms], dtype=torch.float64, device=device)
@@ -343,7 +347,9 @@ def run_gpu(args):
                      "block_residencies": loaded, "block_visits": visits_blocks},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-        "gpu_launches": int(args.steps * (1 + 2 + 2 * st.batches + 4)),
+        # per step on each rank: reset fill (1) + K1 prepare/finalize (2) + per batch [RGBX + LUT] + touch + sort +
+        # integrate + MC neighbours/classify/scan/emit [+ colours]
+        "gpu_launches": int(args.steps * (3 + st.batches * (5 if color else 3) + (5 if color else 4))),
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

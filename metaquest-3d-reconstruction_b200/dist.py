@@ -225,15 +225,18 @@ def _fence_token(dev: torch.device) -> torch.Tensor:
     return _FENCE[key]
 
 
-def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangles: torch.Tensor, dst: int = 0):
+def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangles: torch.Tensor, dst: int = 0,
+                colors: Optional[torch.Tensor] = None):
     """Concatenate per-rank meshes on `dst`: vertex arrays are appended in rank order and triangle
     indices rebased by the exclusive scan of the per-rank vertex counts.  Returns (vertices, normals,
-    triangles, counts [world,2]) on dst and (None, None, None, counts) elsewhere.  Vertices on edges owned
-    by ghost blocks are emitted by every rank that references them (no welding)."""
+    triangles, counts [world,2]) on dst and (None, None, None, counts) elsewhere; with `colors` (per-vertex
+    float32 [V,3]) a fifth element carries the gathered colours.  Vertices on edges owned by ghost blocks are
+    emitted by every rank that references them (no welding)."""
     import torch.distributed as dist
+    extra = () if colors is None else (colors,)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         counts = torch.tensor([[vertices.shape[0], triangles.shape[0]]], dtype=torch.int64)
-        return vertices, normals, triangles, counts
+        return (vertices, normals, triangles, counts) + extra
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = vertices.device
     mine = torch.tensor([vertices.shape[0], triangles.shape[0]], dtype=torch.int64, device=dev)
@@ -242,40 +245,33 @@ def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangl
     counts_h = counts.cpu()
     nv, nt = counts_h[:, 0].tolist(), counts_h[:, 1].tolist()
     # exact-size point-to-point transfers straight into slices of the destination arrays (one NCCL group,
-    # no padding, no concatenation); every rank must agree on whether normals travel
-    has_normals = normals is not None
+    # no padding, no concatenation); every rank must agree on which per-vertex arrays travel
+    per_vertex = [vertices, normals, colors]           # None entries stay None in the result
     if rank != dst:
-        ops = []
-        if nv[rank]:
-            ops.append(dist.P2POp(dist.isend, vertices.contiguous(), dst))
-            if has_normals:
-                ops.append(dist.P2POp(dist.isend, normals.contiguous(), dst))
+        ops = [dist.P2POp(dist.isend, a.contiguous(), dst) for a in per_vertex if a is not None and nv[rank]]
         if nt[rank]:
             ops.append(dist.P2POp(dist.isend, triangles.contiguous(), dst))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        return None, None, None, counts_h
+        return (None, None, None, counts_h) + ((None,) if colors is not None else ())
     voff = [0] * (world + 1)
     toff = [0] * (world + 1)
     for r in range(world):
         voff[r + 1], toff[r + 1] = voff[r] + nv[r], toff[r] + nt[r]
-    v = torch.empty((voff[world], 3), dtype=torch.float32, device=dev)
-    n = torch.empty((voff[world], 3), dtype=torch.float32, device=dev) if has_normals else None
+    out = [None if a is None else torch.empty((voff[world], 3), dtype=a.dtype, device=dev) for a in per_vertex]
     t = torch.empty((toff[world], 3), dtype=triangles.dtype, device=dev)
     ops = []
     for r in range(world):
         vs, ts = slice(voff[r], voff[r + 1]), slice(toff[r], toff[r + 1])
         if r == rank:
-            v[vs] = vertices
-            if has_normals:
-                n[vs] = normals
+            for o, a in zip(out, per_vertex):
+                if o is not None:
+                    o[vs] = a
             t[ts] = triangles
             continue
         if nv[r]:
-            ops.append(dist.P2POp(dist.irecv, v[vs], r))
-            if has_normals:
-                ops.append(dist.P2POp(dist.irecv, n[vs], r))
+            ops += [dist.P2POp(dist.irecv, o[vs], r) for o in out if o is not None]
         if nt[r]:
             ops.append(dist.P2POp(dist.irecv, t[ts], r))
     if ops:
@@ -284,4 +280,4 @@ def gather_mesh(vertices: torch.Tensor, normals: Optional[torch.Tensor], triangl
     for r in range(1, world):
         if nt[r] and voff[r]:
             t[toff[r]:toff[r + 1]] += voff[r]
-    return v, n, t, counts_h
+    return (out[0], out[1], t, counts_h) + ((out[2],) if colors is not None else ())

@@ -123,7 +123,8 @@ def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
     return _COPY_STREAMS[key]
 
 
-def extract_mesh_to_host(vbg: VoxelBlockGrid, weight_threshold: float):
-    """K5 + D2H: (vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3]) as numpy arrays."""
-    v, n, t = vbg.extract_triangle_mesh_arrays(weight_threshold)
-    return v.cpu().numpy(), n.cpu().numpy(), t.cpu().numpy()
+def extract_mesh_to_host(vbg: VoxelBlockGrid, weight_threshold: float, with_colors: bool = False):
+    """K5 + D2H: (vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, colors f32 [V,3]]) as numpy
+    arrays; with_colors needs a grid with the colour attribute."""
+    out = vbg.extract_triangle_mesh_arrays(weight_threshold, with_colors=with_colors)
+    return tuple(a.cpu().numpy() for a in out)
