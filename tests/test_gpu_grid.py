@@ -150,3 +150,39 @@ def test_save_load_roundtrip(cuda_device, oracle, tmp_path):
     b = sort_blocks(*[x.cpu().numpy() for x in g2.export_blocks()[:3]])
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_integrate_shapes_are_bit_identical(cuda_device, oracle, color, monkeypatch):
+    """Every work-item shape of the fused kernel (MQ3D_INTEG_VARIANT: whole / half / quarter / eighth blocks,
+    different CTA sizes) produces the same bits and the same statistics."""
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    from mq3d_b200.vbg import VoxelBlockGrid
+    from helpers import capture, pipeline_cameras, sort_blocks
+    n = 12
+    cap = capture(n)
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = torch.from_numpy(np.stack([oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i]) for i in range(n)])).to(cuda_device)
+    kw = {}
+    if color:
+        f, cw, ch = 110.0, 160, 120
+        cols = np.stack([synth.make_color_frame(Ecw[i], width=cw, height=ch, f=f) for i in range(n)])
+        kw = dict(colors=torch.from_numpy(cols).to(cuda_device),
+                  color_intrinsics=np.tile(np.array([[f, 0, cw / 2.0], [0, f, ch / 2.0], [0, 0, 1.0]]), (n, 1, 1)))
+    attrs = ("tsdf", "weight", "color") if color else ("tsdf", "weight")
+    results = {}
+    for variant in ("0", "9", "8", "12", "1", "3"):
+        monkeypatch.setenv("MQ3D_INTEG_VARIANT", variant)
+        g = VoxelBlockGrid(attr_names=attrs, voxel_size=0.02, block_count=3000, device=cuda_device)
+        st = g.integrate_sequence(lin, K, Ewc, 4.0, 10.0, batch_frames=5, **kw)
+        blocks = sort_blocks(*[x.cpu().numpy() if x is not None else None for x in g.export_blocks()])
+        results[variant] = (st.block_visits, st.voxel_updates, st.num_blocks, blocks)
+    ref = results["9"]
+    for variant, got in results.items():
+        assert got[:3] == ref[:3], variant
+        for a, b in zip(got[3], ref[3]):
+            if a is not None:
+                assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                      b.view(np.uint32) if b.dtype == np.float32 else b), variant
