@@ -284,7 +284,21 @@ def run_gpu(args):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
-    h2d = raw_host.numel() * 4 + (col_host.numel() if color else 0)
+    h2d = raw_host.numel() * 4
+    h2d_note = "depth frames by DMA"
+    if color and world == 1:
+        # zero-copy colour: the resampler reads the pinned frames in place; what crosses PCIe are the 32-byte
+        # sectors of the sampled pixels.  Sampled columns are < 32 B apart, so count every touched row in full.
+        from mq3d_b200 import synth
+        fy, cy = float(wl["K"][0][1, 1]), float(wl["K"][0][1, 2])
+        vf = wl["Kc"][0][1, 1] * ((np.arange(synth.DEPTH_H) - cy) / fy) + wl["Kc"][0][1, 2]
+        rows = np.unique(np.round(vf[(vf >= 0) & (vf <= synth.COLOR_H - 1)]))
+        h2d += n * len(rows) * synth.COLOR_W * 3
+        h2d_note += (f" + colour read in place from pinned host memory by k_color_resample: {len(rows)} of "
+                     f"{synth.COLOR_H} rows per frame touched (full frames would be {col_host.numel()} B)")
+    elif color:
+        h2d += col_host.numel()
+        h2d_note += " + full colour frames, 1/N per rank by DMA, completed by NCCL all-gather"
     hv, ht = host_mesh[0], host_mesh[2]
     d2h = sum(a.nbytes for a in host_mesh)
 
@@ -346,10 +360,10 @@ def run_gpu(args):
                      "frac_batched": batched_bytes / (integ_ms * 1e-3) / 1e9 / peak,
                      "block_residencies": loaded, "block_visits": visits_blocks},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-        # per step on each rank: reset fill (1) + K1 prepare/finalize (2) + per batch [RGBX + LUT] + touch + sort +
-        # integrate + MC neighbours/classify/scan/emit [+ colours]
-        "gpu_launches": int(args.steps * (3 + st.batches * (5 if color else 3) + (5 if color else 4))),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "h2d_note": h2d_note},
+        # per step on each rank: reset fill (1) + K1 prepare/finalize (2) + per batch [colour resample] + touch +
+        # sort + integrate + bitmap clear + MC neighbours/classify/scan/emit [+ colours]
+        "gpu_launches": int(args.steps * (3 + st.batches * (5 if color else 4) + (5 if color else 4))),
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

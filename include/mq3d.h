@@ -160,6 +160,22 @@ int mq3d_integrate_sequence(mq3d_grid *g, const float *depth_dev, const int32_t 
                             const double *E, float depth_scale, float depth_max,
                             float trunc_voxel_multiplier, int batch_frames, mq3d_seq_stats *stats,
                             void *stream);
+/* Colour on the depth pixel grid.  The colour branch of Open3D's Integrate reads, for a voxel that projects
+ * to depth pixel (ui, vi), the colour pixel round(Project_colourK(Unproject_depthK(ui, vi, 1))) under an
+ * identity extrinsic -- a function of the depth pixel alone.  mq3d_color_resample evaluates it once per
+ * frame: rgbx_dev uint32 [n_frames][H][W] = R | G << 8 | B << 16, byte 3 = 0xFF where the projection leaves
+ * the colour image.  color_src: uint8 [n_frames][CH][CW][3] in device memory OR in pinned (mapped) host
+ * memory -- then only the W x H sampled pixels per frame cross PCIe instead of CW x CH.  Asynchronous on
+ * `stream`.  mq3d_integrate_sequence does this internally per batch; mq3d_integrate_sequence_rgbx takes
+ * the resampled frames instead (so that a copy stream can prepare batch k+1 while batch k integrates). */
+int mq3d_color_resample(const uint8_t *color_src, int n_frames, int color_width, int color_height,
+                        int width, int height, const double *Kd, const double *Kc, uint32_t *rgbx_dev,
+                        int device, void *stream);
+int mq3d_integrate_sequence_rgbx(mq3d_grid *g, const float *depth_dev, const int32_t *frame_valid_dev,
+                                 int n_frames, int width, int height, const uint32_t *rgbx_dev,
+                                 const double *Kd, const double *E, float depth_scale, float depth_max,
+                                 float trunc_voxel_multiplier, int batch_frames, mq3d_seq_stats *stats,
+                                 void *stream);
 
 /* ---- K5: marching cubes / point cloud -------------------------------------------------------
  * Replaces vbg.extract_triangle_mesh(weight_threshold, estimated_vertex_number=-1)

@@ -28,6 +28,7 @@ SYMBOLS = [
     "mq3d_grid_set_partition", "mq3d_grid_set_ghost_mode", "mq3d_grid_ghost_select",
     "mq3d_grid_ghost_counts", "mq3d_grid_peer_descriptor", "mq3d_grid_ghost_pull",
     "mq3d_depth_prepare", "mq3d_touch", "mq3d_integrate", "mq3d_integrate_sequence",
+    "mq3d_color_resample", "mq3d_integrate_sequence_rgbx",
     "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_points_count",
     "mq3d_extract_points_fill", "mq3d_extract_mesh_colors", "mq3d_extract_points_colors", "mq3d_confidence",
     "mq3d_scene_create", "mq3d_scene_destroy", "mq3d_scene_add_triangles",
@@ -85,6 +86,9 @@ def lib() -> C.CDLL:
         "mq3d_integrate": [vp, vp, i64, vp, i32, i32, vp, i32, i32, pd, pd, pd, f32, f32, f32, vp],
         "mq3d_integrate_sequence": [vp, vp, vp, i32, i32, i32, vp, i32, i32, pd, pd, pd, f32, f32, f32, i32,
                                     C.POINTER(SeqStats), vp],
+        "mq3d_color_resample": [vp, i32, i32, i32, i32, i32, pd, pd, vp, i32, vp],
+        "mq3d_integrate_sequence_rgbx": [vp, vp, vp, i32, i32, i32, vp, pd, pd, f32, f32, f32, i32,
+                                         C.POINTER(SeqStats), vp],
         "mq3d_extract_mesh_count": [vp, f32, C.POINTER(i64), C.POINTER(i64), vp],
         "mq3d_extract_mesh_fill": [vp, vp, vp, vp, vp, vp],
         "mq3d_extract_points_count": [vp, f32, C.POINTER(i64), vp],

@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .vbg import SequenceStats, VoxelBlockGrid, depth_prepare
+from .vbg import SequenceStats, VoxelBlockGrid, color_resample, depth_prepare
 
 
 @dataclass
@@ -42,13 +42,16 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     """Integrate [F,H,W] raw NDC depth frames (host, ideally pinned) into `vbg`.
 
     conf/count (float64 / int32 [F,H,W], host or device) enable the reference's confidence mask
-    (o3d_utils.py:131-142).  colors_host: uint8 [F,CH,CW,3] enables Open3D's colour overload.
+    (o3d_utils.py:131-142).  colors_host: uint8 [F,CH,CW,3] enables Open3D's colour overload.  Colour never
+    travels as whole frames when it is pinned: the copy stream resamples each chunk onto the depth pixel grid
+    (mq3d_color_resample) reading the pinned frames in place, so only the W x H sampled pixels per frame
+    cross PCIe; unpinned colour is copied to the device first.
 
     shard=(rank, world): multi-GPU upload.  Every rank integrates every frame into its own blocks, but each
     rank moves only 1/world of each chunk over its PCIe link and the chunk is completed by an NCCL
     all-gather over NVLink (the frame broadcast of SURVEY 8e, sharded), still on the copy stream."""
     dev = vbg.device
-    F = int(raw_host.shape[0])
+    F, H, W = (int(x) for x in raw_host.shape)
     if shard is not None and int(shard[1]) > 1:
         import torch.distributed as dist
         s_rank, s_world = int(shard[0]), int(shard[1])
@@ -84,7 +87,11 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
         with torch.cuda.stream(copy):
             part = {"raw": upload(raw_host, f0, f1)}
             if use_color:
-                part["col"] = upload(colors_host, f0, f1)
+                zero_copy = shard is None and colors_host.device.type == "cpu" and colors_host.is_pinned()
+                src = colors_host[f0:f1] if zero_copy else upload(colors_host, f0, f1)
+                part["rgbx"] = color_resample(src.contiguous(), K[f0:f1], np.asarray(Kc)[f0:f1], W, H, device=dev)
+                if not zero_copy:
+                    src.record_stream(copy)
             if mask:
                 for name, src in (("conf", conf), ("count", count)):
                     part[name] = upload(src, f0, f1) if src.device.type == "cpu" else src[f0:f1].to(dev)
@@ -100,9 +107,7 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
                                    None if (has_conf is None or not mask) else has_conf[f0:f1],
                                    params.confidence_threshold, params.valid_count_threshold)
         st = vbg.integrate_sequence(lin, K[f0:f1], E_wc[f0:f1], params.depth_max, params.trunc_voxel_multiplier, 1.0,
-                                    frame_valid=valid, colors=part.get("col"),
-                                    color_intrinsics=None if Kc is None else np.asarray(Kc)[f0:f1],
-                                    batch_frames=chunk)
+                                    frame_valid=valid, colors_rgbx=part.get("rgbx"), batch_frames=chunk)
         if total is None:
             total = st
         else:

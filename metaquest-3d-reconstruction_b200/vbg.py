@@ -126,6 +126,7 @@ class VoxelBlockGrid:
                                                    mask, self.device_index, C.byref(h)))
         self._h = h
         self._keys_scratch: Optional[torch.Tensor] = None
+        self.partition = None      # (rank, world, tile_blocks, integrate_ghosts) once set_partition was called
 
     # -- life cycle ---------------------------------------------------------------------------------
     def close(self):
@@ -289,8 +290,13 @@ class VoxelBlockGrid:
     def integrate_sequence(self, depths: torch.Tensor, intrinsics, extrinsics, depth_max: float,
                            trunc_voxel_multiplier: float, depth_scale: float = 1.0,
                            frame_valid: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
-                           color_intrinsics=None, batch_frames: int = 64) -> SequenceStats:
-        """Fused frame loop of ``integrate()`` (o3d_utils.py:231-236) over [F,H,W] linear depth."""
+                           color_intrinsics=None, batch_frames: int = 64,
+                           colors_rgbx: Optional[torch.Tensor] = None) -> SequenceStats:
+        """Fused frame loop of ``integrate()`` (o3d_utils.py:231-236) over [F,H,W] linear depth.
+
+        colors: uint8 [F,CH,CW,3], a CUDA tensor or a *pinned* CPU tensor (read in place over PCIe: only the
+        W x H sampled pixels per frame travel); other CPU tensors are copied to the device first.
+        colors_rgbx: int32 [F,H,W] from color_resample() instead of colors (+ color_intrinsics)."""
         if depths.dim() != 3 or depths.dtype != torch.float32 or not depths.is_cuda:
             raise RuntimeError("depths must be a float32 CUDA tensor [F,H,W]")
         depths = depths.contiguous()
@@ -301,13 +307,25 @@ class VoxelBlockGrid:
         if frame_valid is not None:
             fv = frame_valid.to(self.device).to(torch.int32).contiguous()
         col, Kc, CW, CH = None, Kd, 0, 0
+        st = _lib.SeqStats()
+        if colors_rgbx is not None and self.has_color:
+            if (colors_rgbx.dtype != torch.int32 or tuple(colors_rgbx.shape) != (F, H, W) or not colors_rgbx.is_cuda
+                    or not colors_rgbx.is_contiguous()):
+                raise RuntimeError("colors_rgbx must be a contiguous int32 CUDA tensor [F,H,W] (see color_resample)")
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().mq3d_integrate_sequence_rgbx(
+                    self._h, _lib.dptr(depths), _lib.dptr(fv), F, W, H, _lib.dptr(colors_rgbx), _lib.darr(Kd),
+                    _lib.darr(E), C.c_float(depth_scale), C.c_float(depth_max), C.c_float(trunc_voxel_multiplier),
+                    int(batch_frames), C.byref(st), _stream()))
+            return SequenceStats(st.frames_integrated, st.block_visits, st.blocks_loaded, st.num_blocks, st.batches,
+                                 st.voxel_updates, st.touch_ms, st.integrate_ms)
         if colors is not None and self.has_color:
             if colors.dtype != torch.uint8 or colors.dim() != 4 or colors.shape[0] != F or colors.shape[3] != 3:
                 raise RuntimeError("colors must be uint8 [F,H,W,3]")
-            col = colors.to(self.device).contiguous()
+            zero_copy = colors.device.type == "cpu" and colors.is_pinned() and colors.is_contiguous()
+            col = colors if zero_copy else colors.to(self.device).contiguous()
             CH, CW = int(col.shape[1]), int(col.shape[2])
             Kc = _as_np(color_intrinsics, np.float64, (F, 3, 3))
-        st = _lib.SeqStats()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mq3d_integrate_sequence(
                 self._h, _lib.dptr(depths), _lib.dptr(fv), F, W, H, _lib.dptr(col), CW, CH, _lib.darr(Kd),
@@ -430,6 +448,30 @@ class VoxelBlockGrid:
         from .geometry import PointCloud
         out = self.extract_point_cloud_arrays(weight_threshold, with_colors=self.has_color)
         return PointCloud(out[0], out[1], out[2] if self.has_color else None)
+
+
+def color_resample(colors: torch.Tensor, depth_intrinsics, color_intrinsics, width: int, height: int,
+                   device=None) -> torch.Tensor:
+    """Colour frames resampled onto the depth pixel grid (mq3d_color_resample): int32 [F,height,width] CUDA
+    tensor, R | G<<8 | B<<16, byte 3 = 0xFF where the depth pixel projects outside the colour image.
+    colors: uint8 [F,CH,CW,3] on the GPU or in *pinned* host memory (read in place over PCIe: only the sampled
+    pixels travel).  Asynchronous on the current stream."""
+    if colors.dtype != torch.uint8 or colors.dim() != 4 or colors.shape[3] != 3 or not colors.is_contiguous():
+        raise RuntimeError("colors must be a contiguous uint8 tensor [F,CH,CW,3]")
+    if colors.is_cuda:
+        device = colors.device
+    elif not colors.is_pinned():
+        raise RuntimeError("host colour frames must be pinned (torch.Tensor.pin_memory) to be read by the GPU")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    F, CH, CW = int(colors.shape[0]), int(colors.shape[1]), int(colors.shape[2])
+    Kd = _as_np(depth_intrinsics, np.float64, (F, 3, 3))
+    Kc = _as_np(color_intrinsics, np.float64, (F, 3, 3))
+    out = torch.empty((F, int(height), int(width)), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().mq3d_color_resample(C.c_void_p(colors.data_ptr()), F, CW, CH, int(width), int(height),
+                                                  _lib.darr(Kd), _lib.darr(Kc), _lib.dptr(out), int(device.index),
+                                                  _stream()))
+    return out
 
 
 def depth_prepare(raw: torch.Tensor, nears, fars, conf: Optional[torch.Tensor] = None,

@@ -107,3 +107,45 @@ def test_depth_scale_is_applied(cuda_device, oracle):
     k0, t0, w0 = sort_blocks(*og.export()[:3])
     k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
     assert np.array_equal(k0, k1) and np.array_equal(w0, w1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+
+
+def test_color_resample_paths_agree(cuda_device, oracle):
+    """Colour on the depth grid: the resampler gives the same image from device memory and from pinned host
+    memory read in place (zero-copy), matches a NumPy restatement of the look-up, and integrating the
+    pre-resampled frames (or pinned frames directly) is bit-identical to integrating the raw device frames."""
+    from mq3d_b200.vbg import VoxelBlockGrid, color_resample
+    lin, K, Ewc, colors, Kc = _setup(oracle, n=5, cw=161, ch=119)        # odd sizes: unaligned rows
+    n, H, W = lin.shape
+    dev_cols = torch.from_numpy(colors).to(cuda_device)
+    pin_cols = torch.from_numpy(colors).pin_memory()
+    a = color_resample(dev_cols, K, Kc, W, H)
+    b = color_resample(pin_cols, K, Kc, W, H, device=cuda_device)
+    torch.cuda.synchronize()
+    assert a.dtype == torch.int32 and tuple(a.shape) == (n, H, W) and torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        color_resample(torch.from_numpy(colors), K, Kc, W, H)             # pageable host memory is refused
+    # NumPy restatement (float32 arithmetic of TransformIndexer Unproject / Project, round half away from zero)
+    got = a.cpu().numpy().view(np.uint32)
+    for f in range(n):
+        fx, fy, cx, cy = (np.float32(K[f][0, 0]), np.float32(K[f][1, 1]), np.float32(K[f][0, 2]), np.float32(K[f][1, 2]))
+        cfx, cfy, ccx, ccy = (np.float32(Kc[f][0, 0]), np.float32(Kc[f][1, 1]), np.float32(Kc[f][0, 2]), np.float32(Kc[f][1, 2]))
+        uf = cfx * ((np.arange(W, dtype=np.float32) - cx) / fx) + ccx
+        vf = cfy * ((np.arange(H, dtype=np.float32) - cy) / fy) + ccy
+        rnd = lambda x: np.where(x >= 0, np.floor(x + np.float32(0.5)), np.ceil(x - np.float32(0.5))).astype(np.int64)
+        u_ok, v_ok = (uf >= 0) & (uf <= colors.shape[2] - 1), (vf >= 0) & (vf <= colors.shape[1] - 1)
+        cu, cv = np.clip(rnd(uf), 0, colors.shape[2] - 1), np.clip(rnd(vf), 0, colors.shape[1] - 1)
+        px = colors[f][cv[:, None], cu[None, :]].astype(np.uint32)
+        want = px[..., 0] | (px[..., 1] << 8) | (px[..., 2] << 16)
+        want = np.where(v_ok[:, None] & u_ok[None, :], want, np.uint32(0xFF000000))
+        assert np.array_equal(got[f], want), f
+    assert (got >> 24 == 0).mean() > 0.3 and (got >> 24 != 0).any()          # both inside and outside occur
+    d = torch.from_numpy(lin).to(cuda_device)
+    grids = []
+    for kw in (dict(colors=dev_cols, color_intrinsics=Kc), dict(colors_rgbx=a), dict(colors=pin_cols, color_intrinsics=Kc)):
+        g = VoxelBlockGrid(attr_names=("tsdf", "weight", "color"), voxel_size=0.02, block_count=500, device=cuda_device)
+        g.integrate_sequence(d, K, Ewc, 4.0, 10.0, batch_frames=2, **kw)
+        grids.append(sort_blocks(*[x.cpu().numpy() for x in g.export_blocks()]))
+    for other in grids[1:]:
+        for x, y in zip(grids[0], other):
+            assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x,
+                                  y.view(np.uint32) if y.dtype == np.float32 else y)
