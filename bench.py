@@ -270,8 +270,8 @@ def run_gpu(args):
         if rank != 0:
             torch.cuda.synchronize()
             return (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
-        host = (got[0].cpu().numpy(), got[1].cpu().numpy(), got[2].cpu().numpy())
-        return host + ((got[4].cpu().numpy(),) if color else ())
+        from mq3d_b200.pipeline import to_host
+        return to_host((got[0], got[1], got[2]) + ((got[4],) if color else ()))
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()

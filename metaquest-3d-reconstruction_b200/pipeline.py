@@ -87,11 +87,23 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
         with torch.cuda.stream(copy):
             part = {"raw": upload(raw_host, f0, f1)}
             if use_color:
-                zero_copy = shard is None and colors_host.device.type == "cpu" and colors_host.is_pinned()
-                src = colors_host[f0:f1] if zero_copy else upload(colors_host, f0, f1)
-                part["rgbx"] = color_resample(src.contiguous(), K[f0:f1], np.asarray(Kc)[f0:f1], W, H, device=dev)
-                if not zero_copy:
-                    src.record_stream(copy)
+                pinned = colors_host.device.type == "cpu" and colors_host.is_pinned()
+                Kc_np = np.asarray(Kc)
+                if pinned and shard is not None and int(shard[1]) > 1:
+                    # each rank resamples its 1/world of the chunk straight from its pinned frames; the
+                    # all-gather then moves W x H x 4 B per frame over NVLink instead of whole colour frames
+                    per = -(-(f1 - f0) // s_world)
+                    full = torch.empty((per * s_world, H, W), dtype=torch.int32, device=dev)
+                    a = min(f1, f0 + s_rank * per)
+                    b = min(f1, a + per)
+                    mine = full[s_rank * per:(s_rank + 1) * per]
+                    if b > a:
+                        color_resample(colors_host[a:b], K[a:b], Kc_np[a:b], W, H, device=dev, out=mine[: b - a])
+                    dist.all_gather_into_tensor(full, mine)
+                    part["rgbx"] = full[: f1 - f0]
+                else:
+                    src = colors_host[f0:f1] if pinned else upload(colors_host, f0, f1)
+                    part["rgbx"] = color_resample(src.contiguous(), K[f0:f1], Kc_np[f0:f1], W, H, device=dev)
             if mask:
                 for name, src in (("conf", conf), ("count", count)):
                     part[name] = upload(src, f0, f1) if src.device.type == "cpu" else src[f0:f1].to(dev)
@@ -128,8 +140,20 @@ def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
     return _COPY_STREAMS[key]
 
 
+def to_host(tensors):
+    """Device tensors -> numpy arrays through pinned staging (torch's caching host allocator reuses the blocks),
+    all copies in flight together, one synchronisation."""
+    outs = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream().synchronize()
+    return tuple(h.numpy() for h in outs)
+
+
 def extract_mesh_to_host(vbg: VoxelBlockGrid, weight_threshold: float, with_colors: bool = False):
     """K5 + D2H: (vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, colors f32 [V,3]]) as numpy
     arrays; with_colors needs a grid with the colour attribute."""
-    out = vbg.extract_triangle_mesh_arrays(weight_threshold, with_colors=with_colors)
-    return tuple(a.cpu().numpy() for a in out)
+    with torch.cuda.device(vbg.device):
+        return to_host(vbg.extract_triangle_mesh_arrays(weight_threshold, with_colors=with_colors))

@@ -451,7 +451,7 @@ class VoxelBlockGrid:
 
 
 def color_resample(colors: torch.Tensor, depth_intrinsics, color_intrinsics, width: int, height: int,
-                   device=None) -> torch.Tensor:
+                   device=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Colour frames resampled onto the depth pixel grid (mq3d_color_resample): int32 [F,height,width] CUDA
     tensor, R | G<<8 | B<<16, byte 3 = 0xFF where the depth pixel projects outside the colour image.
     colors: uint8 [F,CH,CW,3] on the GPU or in *pinned* host memory (read in place over PCIe: only the sampled
@@ -466,7 +466,13 @@ def color_resample(colors: torch.Tensor, depth_intrinsics, color_intrinsics, wid
     F, CH, CW = int(colors.shape[0]), int(colors.shape[1]), int(colors.shape[2])
     Kd = _as_np(depth_intrinsics, np.float64, (F, 3, 3))
     Kc = _as_np(color_intrinsics, np.float64, (F, 3, 3))
-    out = torch.empty((F, int(height), int(width)), dtype=torch.int32, device=device)
+    if out is None:
+        out = torch.empty((F, int(height), int(width)), dtype=torch.int32, device=device)
+    elif (out.dtype != torch.int32 or tuple(out.shape) != (F, int(height), int(width)) or not out.is_cuda
+          or not out.is_contiguous()):
+        raise RuntimeError("out must be a contiguous int32 CUDA tensor [F,height,width]")
+    if F == 0:
+        return out
     with torch.cuda.device(device):
         _lib.check(_lib.lib().mq3d_color_resample(C.c_void_p(colors.data_ptr()), F, CW, CH, int(width), int(height),
                                                   _lib.darr(Kd), _lib.darr(Kc), _lib.dptr(out), int(device.index),

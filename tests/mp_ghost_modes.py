@@ -87,6 +87,18 @@ def main():
     gd = make(True, 4000)
     integrate_frames(gd, raw_host, ds.nears, ds.fars, K, Ewc, params, colors_host=col_host, Kc=Kc, shard=(rank, world))
     assert same(ref, blocks(gd)), f"rank {rank}: sharded upload differs"
+    # pageable colour takes the copy-then-resample route; the mesh read-back goes through pinned staging
+    ge = make(True, 4000)
+    integrate_frames(ge, raw_host, ds.nears, ds.fars, K, Ewc, params, colors_host=torch.from_numpy(cols_np), Kc=Kc,
+                     shard=(rank, world))
+    assert same(ref, blocks(ge)), f"rank {rank}: sharded upload of pageable colour differs"
+    from mq3d_b200.pipeline import extract_mesh_to_host
+    host_mesh = extract_mesh_to_host(ge, 1.5, with_colors=True)
+    # (block order, hence vertex order, depends on the allocation order: compare as sets keyed by position)
+    oa, ob = np.lexsort(host_mesh[0].T[::-1]), np.lexsort(ref_mesh[0].T[::-1])
+    for i in (0, 1, 3):
+        assert np.array_equal(host_mesh[i][oa].view(np.uint32), ref_mesh[i][ob].view(np.uint32)), i
+    assert host_mesh[2].shape == ref_mesh[2].shape
     # gather: rank 0 ends up with every rank's vertices / triangles, indices rebased
     v, nrm, t = ga.extract_triangle_mesh_arrays(1.5)
     gv, gn, gt, counts = gather_mesh(v, nrm, t, dst=0)
