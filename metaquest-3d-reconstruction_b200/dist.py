@@ -175,11 +175,11 @@ def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fe
     except Exception as e:                      # e.g. CUDA IPC not permitted in this container
         ok, err = 0, e
         mine = torch.zeros(PEER_DESC_BYTES, dtype=torch.uint8, device=dev)
-    table = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
+    table = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)     # flat: valid for NCCL and gloo
     dist.all_gather_into_tensor(table, mine)
     if ok:
         try:
-            n = vbg.ghost_pull(table.cpu().numpy())
+            n = vbg.ghost_pull(table.cpu().numpy().reshape(world, mine.numel()))
         except Exception as e:
             ok, err = 0, e
     # the fence doubles as the status exchange: every rank learns whether every pull was issued

@@ -105,3 +105,70 @@ def _ghost_worker(rank, world, port, out_dir):
 def test_ghost_exchange_world2(tmp_path):
     mp.spawn(_ghost_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+class _NoIpcGrid(_FakeGrid):
+    """A grid whose peer-memory path is unavailable on ONE rank only (e.g. CUDA IPC refused in a container)."""
+    device = "cpu"
+
+    def peer_descriptor(self):
+        if self.rank == 1:
+            raise RuntimeError("cudaIpcGetMemHandle -> operation not supported")
+        return np.zeros(512, np.uint8)
+
+    def ghost_pull(self, descs):
+        raise AssertionError("must not be reached: rank 1 published no descriptor, so rank 0's pull is rejected")
+
+
+class _BadPullGrid(_FakeGrid):
+    """Descriptors are fine, but opening a peer's pool fails on rank 0."""
+    device = "cpu"
+
+    def peer_descriptor(self):
+        return np.full(512, self.rank + 1, np.uint8)
+
+    def ghost_pull(self, descs):
+        assert descs.shape == (self.world, 512) and descs[0, 0] == 1 and descs[1, 0] == 2   # rank order
+        if self.rank == 0:
+            raise RuntimeError("cudaIpcOpenMemHandle -> invalid device context")
+        return 0
+
+
+def _fallback_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import dist as mqd
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    other = 1 - rank
+    want = [(other, i, 0) for i in range(3 + other) if (i + rank) % 2 == 0]
+    # (1) a failing pull on one rank raises PeerPullError on BOTH ranks (nobody is left waiting in a collective)
+    g = _BadPullGrid(rank, world)
+    try:
+        mqd.pull_ghosts(g, rank, world)
+        raise AssertionError("pull_ghosts should have raised")
+    except mqd.PeerPullError:
+        pass
+    # (2) fill_ghost_shell then falls back to the NCCL/gloo exchange on every rank, and remembers it
+    mqd._PULL_USABLE[0] = True
+    g = _NoIpcGrid(rank, world) if rank == 1 else _NoIpcGridRank0(rank, world)
+    assert mqd.fill_ghost_shell(g, rank, world, "pull") == "exchange"
+    for key in want:
+        assert key in g.blocks and float(g.blocks[key][0][7]) == 10 * other + key[1]
+    assert mqd._PULL_USABLE[0] is False
+    g2 = _FakeGrid(rank, world)                       # no peer_descriptor at all: would fail if pull were retried
+    assert mqd.fill_ghost_shell(g2, rank, world, "pull") == "exchange"
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+class _NoIpcGridRank0(_NoIpcGrid):
+    def ghost_pull(self, descs):
+        # rank 1's row is all zeros (no descriptor): the real library rejects it ("bad peer descriptor")
+        assert not descs[1].any()
+        raise RuntimeError("bad peer descriptor")
+
+
+def test_ghost_pull_failure_falls_back_on_all_ranks(tmp_path):
+    mp.spawn(_fallback_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
