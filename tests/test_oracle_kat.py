@@ -214,3 +214,51 @@ def test_confidence_static_camera(oracle):
     assert (count[:, :3, :] == 0).all() and (conf[:, :3, :] == 0).all()
     # bilinear taps need u1 < W, v1 < H: the last row/column never validates
     assert (count[:, -1, :] == 0).all() and (count[:, :, -1] == 0).all()
+
+
+def test_color_branch_closed_form(oracle):
+    """Colour branch of Integrate: the colour of a voxel that projects to depth pixel
+    (ui, vi) = (int u, int v) comes from colour pixel round(colourK . depthK^-1 . (ui, vi, 1)) -- a function of
+    the depth pixel alone -- and is averaged with the voxel's weight like the tsdf."""
+    z0, CW, CH, fc = 1.0, 200, 150, 110.0
+    Kc = np.array([[fc, 0, CW / 2.0], [0, fc, CH / 2.0], [0, 0, 1.0]])
+    uu, vv = np.meshgrid(np.arange(CW), np.arange(CH))
+    img = np.stack([uu % 251, vv % 241, (uu + vv) % 239], axis=-1).astype(np.uint8)      # position-coding colours
+    g = oracle.Grid(VS, with_color=True)
+    d = wall(z0)
+    keys = g.touch(d, K, I4, 4.0, TRUNC_MULT)
+    g.integrate(keys, d, K, I4, 4.0, TRUNC_MULT, color=img, Kc=Kc)
+    k2, t2, w2, c2 = g.export()
+    vs = np.float32(VS)
+    checked = 0
+    for i, key in enumerate(k2.tolist()):
+        zz, yy, xx = np.meshgrid(*[np.arange(16, dtype=np.int32)] * 3, indexing="ij")
+        gx = (key[0] * 16 + xx).astype(np.float32) * vs
+        gy = (key[1] * 16 + yy).astype(np.float32) * vs
+        gz = (key[2] * 16 + zz).astype(np.float32) * vs
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = np.float32(1.0) / gz
+            u = np.float32(160.0) * gx * inv + np.float32(160.0)
+            v = np.float32(160.0) * gy * inv + np.float32(160.0)
+        inb = (u >= 0) & (v >= 0) & (u <= 319) & (v <= 319)
+        upd = inb & (gz > 0) & (np.float32(z0) - gz >= -TRUNC)
+        ui, vi = np.where(upd, u, 0).astype(np.int32), np.where(upd, v, 0).astype(np.int32)   # truncation, as (int)u
+        uf = np.float32(fc) * ((ui.astype(np.float32) - np.float32(160.0)) / np.float32(160.0)) + np.float32(CW / 2.0)
+        vf = np.float32(fc) * ((vi.astype(np.float32) - np.float32(160.0)) / np.float32(160.0)) + np.float32(CH / 2.0)
+        cin = upd & (uf >= 0) & (uf <= CW - 1) & (vf >= 0) & (vf <= CH - 1)
+        cu = np.clip(np.floor(uf + np.float32(0.5)), 0, CW - 1).astype(np.int64)          # uf, vf >= 0 where used
+        cv = np.clip(np.floor(vf + np.float32(0.5)), 0, CH - 1).astype(np.int64)
+        want = np.where(cin[..., None], img[cv, cu].astype(np.float32), np.float32(0))
+        assert np.array_equal(c2[i], want), key
+        assert np.array_equal(w2[i], upd.astype(np.float32))
+        checked += int(cin.sum())
+    assert checked > 10000
+    # second frame with another image: colour is the weight-averaged running mean (w = 1 -> (c + c2) / 2)
+    img2 = (255 - img).astype(np.uint8)
+    g.integrate(keys, d, K, I4, 4.0, TRUNC_MULT, color=img2, Kc=Kc)
+    _, _, w3, c3 = g.export()
+    both = (w3 == 2)[..., None] & (c2 + (255 - c2) != 0)
+    mean = (np.float32(1) * c2 + (np.float32(255) - c2)) * (np.float32(1) / np.float32(2))
+    sel = (w3 == 2) & (w2 == 1)
+    cin_any = c2.sum(-1) > 0
+    assert np.array_equal(c3[sel & cin_any], mean[sel & cin_any]) and both.any()
