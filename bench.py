@@ -6,12 +6,14 @@ prints ONE JSON line on rank 0.  A "step" = one pass of the hot path over the wh
 sequence of the workload: grid reset -> K1 (linearise) -> K2+K3 (fused touch/integrate, colour) ->
 K5 (marching cubes).  Workload at every N: BASELINE.json configs[1] (300 left-eye 320x320 depth
 frames + 1280x960 RGB, voxel 0.01 m, 16^3 blocks, trunc x10, depth_max 4 m, weight_threshold 1.5).
-N > 1: voxel blocks are hash-partitioned across ranks; every rank receives the frames
-by NCCL broadcast, integrates the blocks it owns (+ghost shell), extracts its part of the mesh, and
-rank 0 gathers vertex/triangle counts -- strong scaling of one capture.
+N > 1: voxel blocks are hash-partitioned across ranks; every rank holds the frames (NCCL
+broadcast at set-up), integrates the blocks it owns, fetches the one-block ghost shell from the owners'
+pools over NVLink peer memory (or by NCCL exchange / redundant integration, --ghosts), extracts its part
+of the mesh, and rank 0 gathers vertices / normals / colours / triangles -- strong scaling of one capture.
 
 value      = depth frames/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
-e2e        = same metric through the public host-buffer API (pinned host -> H2D -> ... -> mesh D2H)
+e2e        = same metric through the public host-buffer API: pinned host frames -> depth by DMA, colour
+             read in place by the resampler (N > 1: 1/N per rank + NCCL all-gather) -> ... -> mesh on the host
 roofline   = dominant kernel (k_integrate): algorithmic bytes (40 B/voxel-visit with
              colour, 16 B without, + frame images + keys) / its device time (CUDA events recorded
              inside libmq3d on the launching stream) vs MEASURED_PEAKS.json
