@@ -360,7 +360,9 @@ def run_gpu(args):
                              "DRAM traffic is lower than this and frac can exceed 1",
                      "achieved_batched": batched_bytes / (integ_ms * 1e-3) / 1e9,
                      "frac_batched": batched_bytes / (integ_ms * 1e-3) / 1e9 / peak,
-                     "block_residencies": loaded, "block_visits": visits_blocks},
+                     "block_residencies": loaded, "block_visits": visits_blocks,
+                     "launches_per_step": int(st.batches),
+                     "algorithmic_bytes_per_launch": algo_bytes / max(int(st.batches), 1)},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "h2d_note": h2d_note},
         # per step on each rank: reset fill (1) + K1 prepare/finalize (2) + per batch [colour resample] + touch +
