@@ -89,16 +89,34 @@ class DepthDataIO:
         lookup = {}
         if cached is not None:
             lookup = {int(t): i for i, t in enumerate(cached[0])}
+        todo = []
         for i, t in enumerate(ts):
             j = lookup.get(int(t))
             if j is not None:
                 raw[i] = cached[1][j]
                 present[i] = True
-                continue
-            a = self.load_raw_depth_map(side, t, W, H)
-            if a is not None:
-                raw[i] = a
-                present[i] = True
+            else:
+                todo.append(i)
+
+        def read(i):           # straight into row i of the batch; file reads release the GIL
+            p = self.depth_map_path(side, ts[i])
+            if not p.exists():
+                return i, False
+            a = np.fromfile(p, dtype="<f4")
+            if a.size != H * W:
+                raise RuntimeError(f"{p}: expected {H * W} float32 values, found {a.size}")
+            raw[i] = a.reshape(H, W)
+            return i, True
+
+        if len(todo) > 8:      # the file reads of a whole side overlap instead of queueing
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+                done = list(pool.map(read, todo))
+        else:
+            done = [read(i) for i in todo]
+        for i, ok in done:
+            present[i] = ok
         return raw, present
 
     # -- confidence maps ----------------------------------------------------------------------------------

@@ -101,3 +101,27 @@ def test_synthetic_capture_is_valid_quest_shaped():
     assert (cap.raw >= 0).all() and (cap.raw <= 1).all()      # never closer than the near plane
     assert 0.005 < (cap.raw == 1.0).mean() < 0.05              # ~2 % dropped pixels
     assert np.array_equal(np.diff(cap.dataset.timestamps)[:3], [33, 34, 33])
+
+
+def test_raw_sequence_loader_batches_and_flags_missing(tmp_path):
+    """load_raw_sequence reads a whole side into one [N,H,W] batch (threaded file reads), zero-fills and flags
+    frames whose file is missing, and rejects truncated files."""
+    n = 20
+    caps = synth.write_project(tmp_path, n, width=32, height=32)
+    io = DataIO(tmp_path)
+    ds = caps[Side.LEFT].dataset                              # (building it from the CSV validates on the GPU)
+    raw, present = io.depth.load_raw_sequence(Side.LEFT, ds)
+    assert raw.shape == (len(ds), 32, 32) and raw.dtype == np.float32 and present.all()
+    lookup = {int(t): i for i, t in enumerate(caps[Side.LEFT].dataset.timestamps)}
+    for i, t in enumerate(ds.timestamps):
+        assert np.array_equal(raw[i], caps[Side.LEFT].raw[lookup[int(t)]])
+    io.depth.depth_map_path(Side.LEFT, ds.timestamps[3]).unlink()
+    io.depth._raw_cache.clear()
+    raw2, present2 = io.depth.load_raw_sequence(Side.LEFT, ds)
+    assert not present2[3] and present2.sum() == len(ds) - 1 and not raw2[3].any()
+    assert np.array_equal(raw2[4], raw[4])
+    p = io.depth.depth_map_path(Side.LEFT, ds.timestamps[5])
+    p.write_bytes(p.read_bytes()[:100])
+    io.depth._raw_cache.clear()
+    with pytest.raises(RuntimeError, match="expected 1024 float32"):
+        io.depth.load_raw_sequence(Side.LEFT, ds)
