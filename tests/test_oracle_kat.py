@@ -262,3 +262,49 @@ def test_color_branch_closed_form(oracle):
     sel = (w3 == 2) & (w2 == 1)
     cin_any = c2.sum(-1) > 0
     assert np.array_equal(c3[sel & cin_any], mean[sel & cin_any]) and both.any()
+
+
+def test_edge_cases_empty_ragged_extreme(oracle):
+    """Empty grid, frames that touch nothing, a single valid pixel, block keys at the ends of the +-2^20 key
+    range, and K1 on degenerate frames."""
+    g = oracle.Grid(VS)
+    assert g.num_blocks == 0
+    v, n, t, vk = g.extract_mesh(3.0)
+    assert v.shape == (0, 3) and t.shape == (0, 3) and vk.shape == (0, 4)
+    assert g.extract_points(3.0)[0].shape == (0, 3)
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        g.touch(np.zeros((320, 320), np.float32), K, I4, 4.0, TRUNC_MULT)      # all pixels invalid
+    one = np.zeros((320, 320), np.float32)
+    one[160, 160] = 1.0                                                          # a single stride-4 sample
+    keys = g.touch(one, K, I4, 4.0, TRUNC_MULT)
+    assert 1 <= len(keys) <= 8 and set(keys[:, 2].tolist()) <= {2, 3}
+    assert g.integrate(keys, one, K, I4, 4.0, TRUNC_MULT) > 0
+    off = np.zeros((320, 320), np.float32)
+    off[161, 161] = 1.0                                                          # not on the stride-4 lattice
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        oracle.Grid(VS).touch(off, K, I4, 4.0, TRUNC_MULT)
+    # keys at the limits of the packed 3 x 21-bit range survive a load / export round trip and extraction
+    lim = (1 << 20) - 1
+    far_keys = np.array([[lim, lim, lim], [-lim - 1, -lim - 1, -lim - 1], [lim - 1, lim, lim], [0, 0, 0]], np.int32)
+    tsdf = np.linspace(-1, 1, 4 * 4096, dtype=np.float32).reshape(4, 16, 16, 16)
+    h = oracle.Grid(VS)
+    h.load(far_keys, tsdf, np.full_like(tsdf, 5.0))
+    k2, t2, w2, _ = h.export()
+    order = {tuple(k): i for i, k in enumerate(k2.tolist())}
+    assert set(order) == {tuple(k) for k in far_keys.tolist()}
+    for i, k in enumerate(far_keys.tolist()):
+        assert np.array_equal(t2[order[tuple(k)]], tsdf[i])
+    v, n, t, vk = h.extract_mesh(3.0)                  # (lim-1, lim, lim) and (lim, lim, lim) are x-neighbours
+    assert np.isfinite(v).all() and (len(t) == 0 or t.max() < len(v))
+    # K1 on degenerate frames (depth_data_io.py:80-85): all zeros / all ones / NaN / negative are rejected
+    ok = np.full((8, 8), 0.5, np.float32)
+    assert oracle.depth_valid(ok)
+    for bad in (np.zeros((8, 8), np.float32), np.ones((8, 8), np.float32)):
+        assert not oracle.depth_valid(bad)
+    for value in (np.nan, -0.25):
+        frame = ok.copy()
+        frame[3, 4] = value
+        assert not oracle.depth_valid(frame)
+    lin = oracle.depth_to_linear(np.array([[1.0, 0.5, 0.0]], np.float32), 0.1, np.inf)
+    # d = 1 (far plane at infinity) maps to 0 = "no measurement", d = 0 to the near plane (depth_utils.py:42-46)
+    assert lin[0, 0] == 0 and lin[0, 1] == np.float32(0.2) and lin[0, 2] == np.float32(0.1)
