@@ -1,0 +1,126 @@
+"""CPU: cross-restatement.  The C oracle and an independently written NumPy mirror of
+DepthTouch / Integrate (oracle/numpy_mirror.py, from the specification in SURVEY Appendix A) must agree bit
+for bit on hypothesis-generated poses, depth images and colour images.  The CUDA kernels are compared with
+the C oracle in the -m gpu tests, which closes the triangle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import numpy_mirror as mirror  # noqa: E402
+
+W, H, CW, CH = 48, 40, 64, 52
+K = np.array([[30.0, 0, 24.0], [0, 30.0, 20.0], [0, 0, 1.0]])
+KC = np.array([[41.0, 0, 31.5], [0, 43.0, 26.0], [0, 0, 1.0]])
+VS, TRUNC_MULT, DEPTH_MAX = 0.04, 4.0, 3.0
+
+
+def _pose(rng):
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    ang = rng.uniform(-0.7, 0.7)
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    E = np.eye(4)
+    E[:3, :3] = R
+    E[:3, 3] = rng.uniform(-0.3, 0.3, size=3)
+    return E.astype(np.float32).astype(np.float64)          # float32-representable, like transforms.py:210-216
+
+
+def _frame(rng):
+    z0 = rng.uniform(0.6, 1.6)
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    d = z0 + 0.15 * np.sin(u / 7.0 + rng.uniform(0, 6)) * np.cos(v / 5.0) + rng.normal(0, 0.004, size=(H, W))
+    d[rng.random((H, W)) < 0.05] = 0.0                      # dropped samples
+    d[rng.random((H, W)) < 0.01] = 3.5                      # beyond depth_max
+    color = rng.integers(0, 256, size=(CH, CW, 3), dtype=np.uint8)
+    return d.astype(np.float32), color
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 2 ** 31 - 1), with_color=st.booleans())
+def test_c_oracle_and_numpy_mirror_agree(oracle, seed, with_color):
+    rng = np.random.default_rng(seed)
+    og = oracle.Grid(VS, with_color=with_color)
+    grid = {}
+    n_updates = 0
+    for _ in range(3):
+        E = _pose(rng)
+        depth, color = _frame(rng)
+        keys_c = og.touch(depth, K, E, DEPTH_MAX, TRUNC_MULT)
+        keys_m = mirror.touch(depth, K, E, VS, DEPTH_MAX, TRUNC_MULT)
+        assert {tuple(k) for k in keys_c.tolist()} == keys_m                       # K2: same block set
+        kw = dict(color=color, Kc=KC) if with_color else {}
+        up_c = og.integrate(keys_c, depth, K, E, DEPTH_MAX, TRUNC_MULT, **kw)
+        up_m = mirror.integrate(grid, keys_c.tolist(), depth, K, E, VS, DEPTH_MAX, TRUNC_MULT, **kw)
+        assert up_c == up_m
+        n_updates += up_c
+    assert n_updates > 0
+    keys, tsdf, weight, col = og.export()
+    assert {tuple(k) for k in keys.tolist()} == set(grid)
+    for i, key in enumerate(keys.tolist()):
+        t, w, c = grid[tuple(key)]
+        assert np.array_equal(weight[i], w), key
+        assert np.array_equal(tsdf[i].view(np.uint32), t.view(np.uint32)), key     # K3: bit-exact
+        if with_color:
+            assert np.array_equal(col[i].view(np.uint32), c.view(np.uint32)), key
+
+
+def test_mirror_rejects_untouched_frame():
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        mirror.touch(np.zeros((H, W), np.float32), K, np.eye(4), VS, DEPTH_MAX, TRUNC_MULT)
+
+
+@settings(max_examples=4, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 2 ** 31 - 1), thr=st.sampled_from([0.5, 1.5]))
+def test_marching_cubes_restatements_agree(oracle, seed, thr):
+    """K5: the C oracle's four-pass ExtractTriangleMesh and the dense NumPy formulation give the same vertex
+    set (lattice-edge keys), bit-identical positions and normals (stale-component behaviour included) and
+    the same triangles, on grids with ragged block coverage (missing neighbours, partially observed voxels)."""
+    from helpers import canonical_mesh
+    rng = np.random.default_rng(seed)
+    og = oracle.Grid(VS)
+    grid = {}
+    for _ in range(3):
+        E = _pose(rng)
+        depth, _ = _frame(rng)
+        keys = og.touch(depth, K, E, DEPTH_MAX, TRUNC_MULT)
+        og.integrate(keys, depth, K, E, DEPTH_MAX, TRUNC_MULT)
+        mirror.integrate(grid, keys.tolist(), depth, K, E, VS, DEPTH_MAX, TRUNC_MULT)
+    ov, on, ot, ok = og.extract_mesh(thr)
+    mv, mn, mt, mk = mirror.extract_mesh(grid, VS, thr)
+    assert len(ov) > 200 and len(ot) > 200
+    a, b = canonical_mesh(ov, ot, ok, on), canonical_mesh(mv, mt, mk, mn)
+    assert np.array_equal(a["keys"], b["keys"])
+    assert np.array_equal(a["tris"], b["tris"])
+    assert np.array_equal(a["verts"].view(np.uint32), b["verts"].view(np.uint32))
+    same = a["normals"].view(np.uint32) == b["normals"].view(np.uint32)
+    assert same.all() or np.array_equal(np.isnan(a["normals"]), np.isnan(b["normals"])) and \
+        np.array_equal(a["normals"][~np.isnan(a["normals"])], b["normals"][~np.isnan(b["normals"])])
+
+
+@settings(max_examples=4, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 2 ** 31 - 1), thr=st.sampled_from([0.5, 1.5]))
+def test_point_cloud_restatements_agree(oracle, seed, thr):
+    """K5 points: same zero-crossing edges, bit-identical positions and normals from both restatements."""
+    from helpers import canonical_points
+    rng = np.random.default_rng(seed)
+    og = oracle.Grid(VS)
+    grid = {}
+    for _ in range(3):
+        E = _pose(rng)
+        depth, _ = _frame(rng)
+        keys = og.touch(depth, K, E, DEPTH_MAX, TRUNC_MULT)
+        og.integrate(keys, depth, K, E, DEPTH_MAX, TRUNC_MULT)
+        mirror.integrate(grid, keys.tolist(), depth, K, E, VS, DEPTH_MAX, TRUNC_MULT)
+    op, on, ok = og.extract_points(thr)
+    mp, mn, mk = mirror.extract_points(grid, VS, thr)
+    assert len(op) > 200
+    a, b = canonical_points(op, ok, on), canonical_points(mp, mk, mn)
+    assert np.array_equal(a["keys"], b["keys"])
+    assert np.array_equal(a["pts"].view(np.uint32), b["pts"].view(np.uint32))
+    assert np.array_equal(a["normals"].view(np.uint32), b["normals"].view(np.uint32))
