@@ -146,50 +146,114 @@ def estimate_depth_confidences(depth_data_io, config, device="CUDA:0", save: boo
     return out
 
 
-def filter_mesh_components(mesh: TriangleMesh, min_triangle_count: int = 2000) -> TriangleMesh:
-    """Drop connected components with fewer than `min_triangle_count` triangles, then remove degenerate
-    and duplicated triangles and unreferenced vertices (o3d_utils.py:241-321).  Host-side (SciPy
-    connected components); SURVEY 8f N1 ranks a device version next."""
+def _cluster_connected_triangles(t: np.ndarray):
+    """Open3D TriangleMesh::ClusterConnectedTriangles: triangles that share an (undirected) EDGE belong to one
+    cluster; clusters are numbered by their lowest triangle index.  Returns (cluster id per triangle, sizes)."""
     from scipy.sparse import coo_matrix
     from scipy.sparse.csgraph import connected_components
+    n = len(t)
+    e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
+    tri = np.tile(np.arange(n), 3)
+    order = np.lexsort((e[:, 1], e[:, 0]))
+    e, tri = e[order], tri[order]
+    same = (e[1:] == e[:-1]).all(1)                       # consecutive entries of one edge: link their triangles
+    g = coo_matrix((np.ones(int(same.sum()), np.int8), (tri[:-1][same], tri[1:][same])), shape=(n, n))
+    _, label = connected_components(g, directed=False)
+    return label, np.bincount(label)
+
+
+def _remove_non_manifold_edges(v: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """Open3D TriangleMesh::RemoveNonManifoldEdges: while an edge has more than two triangles, delete its
+    smallest-area triangles until two are left (edges visited in sorted order; Open3D's order is that of an
+    unordered_map)."""
+    while len(t):
+        e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
+        tri = np.tile(np.arange(len(t)), 3)
+        order = np.lexsort((e[:, 1], e[:, 0]))
+        e, tri = e[order], tri[order]
+        start = np.concatenate([[True], (e[1:] != e[:-1]).any(1)])
+        group = np.cumsum(start) - 1
+        size = np.bincount(group)
+        bad = np.nonzero(size > 2)[0]
+        if len(bad) == 0:
+            break
+        p = v[t].astype(np.float64)
+        area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
+        first = np.nonzero(start)[0]
+        for gi in bad:
+            members = tri[first[gi]: first[gi] + size[gi]]
+            alive = members[area[members] > 0]
+            for _ in range(len(alive) - 2):
+                alive = members[area[members] > 0]
+                area[alive[np.argmin(area[alive])]] = -1.0
+        if not (area < 0).any():
+            break                                          # only zero-area triangles left on the edge
+        t = t[area >= 0]
+    return t
+
+
+def filter_mesh_components(mesh: TriangleMesh, min_triangle_count: int = 2000) -> TriangleMesh:
+    """Drop-in for o3d_utils.filter_mesh_components (:241-321), step for step on the legacy-mesh semantics of
+    Open3D: cluster_connected_triangles (edge adjacency), keep clusters with >= min_triangle_count triangles (or
+    the largest one), remove_unreferenced_vertices (only if something was removed), remove_degenerate_triangles
+    (repeated vertex index), remove_duplicated_triangles (equal up to rotation), remove_duplicated_vertices
+    (identical coordinates; first occurrence kept, which also welds the vertices several ranks re-emit on
+    ghost edges) and remove_non_manifold_edges.  Normals and colours follow their vertices.  Host-side
+    (NumPy / SciPy); SURVEY 8f N1 ranks a device version next."""
     v = mesh.vertex.positions.detach().cpu().numpy()
     t = mesh.triangle.indices.detach().cpu().numpy().astype(np.int64)
-    nrm = None if mesh.vertex.normals is None else mesh.vertex.normals.detach().cpu().numpy()
+    attrs = [None if a is None else a.detach().cpu().numpy() for a in (mesh.vertex.normals, mesh.vertex.colors)]
     if len(t) == 0:
         print("[Warning] Mesh filtering: Input mesh has no triangles, returning as-is")
         return mesh
-    nv = len(v)
-    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
-    g = coo_matrix((np.ones(len(e), np.int8), (e[:, 0], e[:, 1])), shape=(nv, nv))
-    _, vlabel = connected_components(g, directed=False)
-    tlabel = vlabel[t[:, 0]]
-    labels, counts = np.unique(tlabel, return_counts=True)
-    valid = labels[counts >= min_triangle_count]
+    original = len(t)
+    tlabel, counts = _cluster_connected_triangles(t)
+    valid = np.nonzero(counts >= min_triangle_count)[0]
     if len(valid) == 0:
         print(f"[Warning] Mesh filtering: No components have >= {min_triangle_count} triangles. "
               f"Largest component has {counts.max()} triangles.")
         print("[Warning] Mesh filtering: Returning largest component only.")
-        valid = labels[[np.argmax(counts)]]
+        valid = np.array([np.argmax(counts)])
     keep = np.isin(tlabel, valid)
-    t = t[keep]
-    # degenerate + duplicated triangles
-    t = t[(t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2])]
-    _, first = np.unique(np.sort(t, axis=1), axis=0, return_index=True)
-    t = t[np.sort(first)]
-    used = np.zeros(nv, bool)
-    used[t.ravel()] = True
-    remap = np.cumsum(used) - 1
-    removed = len(labels) - len(valid)
+    removed_tris = int(original - keep.sum())
+
+    def compact(v, attrs, t, used):                        # drop the vertices not flagged in `used`
+        remap = np.cumsum(used) - 1
+        return v[used], [None if a is None else a[used] for a in attrs], remap[t]
+
+    if removed_tris > 0:
+        t = t[keep]
+        used = np.zeros(len(v), bool)
+        used[t.ravel()] = True
+        v, attrs, t = compact(v, attrs, t, used)           # remove_unreferenced_vertices
+    t = t[(t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2])]          # degenerate
+    if len(t):                                             # duplicated: equal after rotating the smallest index first
+        k = np.argmin(t, axis=1)
+        rot = np.stack([np.take_along_axis(t, ((k + i) % 3)[:, None], 1)[:, 0] for i in range(3)], axis=1)
+        _, first = np.unique(rot, axis=0, return_index=True)
+        t = t[np.sort(first)]
+    if len(v):                                             # duplicated vertices: identical coordinates
+        _, first, inverse = np.unique(v, axis=0, return_index=True, return_inverse=True)
+        inverse = np.asarray(inverse).reshape(-1)
+        if len(first) != len(v):
+            keep_v = np.zeros(len(v), bool)
+            keep_v[first] = True
+            new_index = (np.cumsum(keep_v) - 1)[first][inverse]      # old vertex -> index of its first occurrence
+            v, attrs, t = v[keep_v], [None if a is None else a[keep_v] for a in attrs], new_index[t]
+    t = _remove_non_manifold_edges(v, t)
+    removed = len(counts) - len(valid)
     if removed > 0:
-        print(f"[Info] Mesh filtering: Found {len(labels)} connected component(s)")
+        print(f"[Info] Mesh filtering: Found {len(counts)} connected component(s)")
         print(f"[Info] Mesh filtering: Removed {removed} small component(s) with < {min_triangle_count} triangles")
-        print(f"[Info] Mesh filtering: Final mesh has {len(t)} triangles (was {len(keep)})")
+        print(f"[Info] Mesh filtering: Removed {removed_tris} triangles from small components")
+        print(f"[Info] Mesh filtering: Kept {len(valid)} component(s) with >= {min_triangle_count} triangles")
+        print(f"[Info] Mesh filtering: Final mesh has {len(t)} triangles (was {original})")
     else:
-        print(f"[Info] Mesh filtering: All {len(labels)} component(s) have >= {min_triangle_count} triangles, "
+        print(f"[Info] Mesh filtering: All {len(counts)} component(s) have >= {min_triangle_count} triangles, "
               f"no filtering needed")
     dev = mesh.device
-    return TriangleMesh(torch.from_numpy(v[used]).to(dev), torch.from_numpy(remap[t].astype(np.int32)).to(dev),
-                        None if nrm is None else torch.from_numpy(nrm[used]).to(dev))
+    up = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    return TriangleMesh(up(v, torch.float32), up(t, torch.int32), up(attrs[0], torch.float32), up(attrs[1], torch.float32))
 
 
 def raycast_in_color_view(scene: RaycastingScene, dataset: CameraDataset) -> Generator[np.ndarray, None, None]:

@@ -125,3 +125,63 @@ def test_raw_sequence_loader_batches_and_flags_missing(tmp_path):
     io.depth._raw_cache.clear()
     with pytest.raises(RuntimeError, match="expected 1024 float32"):
         io.depth.load_raw_sequence(Side.LEFT, ds)
+
+
+def _tetra(offset, scale=1.0):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32) * scale + np.asarray(offset, np.float32)
+    t = np.array([[0, 2, 1], [0, 1, 3], [1, 2, 3], [0, 3, 2]], np.int32)
+    return v, t
+
+
+def _mesh(v, t, with_attrs=True):
+    import torch
+    from mq3d_b200.geometry import TriangleMesh
+    v = np.asarray(v, np.float32)
+    nrm = torch.from_numpy(-v) if with_attrs else None
+    col = torch.from_numpy(np.clip(np.abs(v) / 10.0, 0, 1).astype(np.float32)) if with_attrs else None
+    return TriangleMesh(torch.from_numpy(v), torch.from_numpy(np.asarray(t, np.int32)), nrm, col)
+
+
+def test_filter_mesh_components_follows_open3d_legacy_semantics(capsys):
+    """filter_mesh_components (o3d_utils.py:241-321) on CPU tensors: edge-adjacency clusters, size threshold with the
+    largest-cluster fallback, degenerate / duplicated triangle removal, vertex welding, non-manifold edges."""
+    from mq3d_b200.ops import _cluster_connected_triangles, filter_mesh_components
+    # two tetrahedra that share ONE VERTEX only (same index): edge adjacency keeps them apart
+    va, ta = _tetra((0, 0, 0))
+    vb, tb = _tetra((0, 0, 0), scale=-1.0)
+    v = np.concatenate([va, vb[1:]])                      # vertex 0 is shared
+    tb2 = np.where(tb == 0, 0, tb + 3)
+    t = np.concatenate([ta, tb2])
+    label, counts = _cluster_connected_triangles(t.astype(np.int64))
+    assert counts.tolist() == [4, 4] and label.tolist() == [0] * 4 + [1] * 4
+    # a big component (two tetrahedra welded along a face would be non-manifold; use a strip) and a small one
+    n = 40
+    strip_v = np.array([[i // 2, i % 2, 0] for i in range(2 * n + 2)], np.float32)
+    strip_t = np.array([[i, i + 1, i + 2] if i % 2 == 0 else [i + 1, i, i + 2] for i in range(2 * n)], np.int32)
+    far_v, far_t = _tetra((100, 0, 0))
+    v = np.concatenate([strip_v, far_v])
+    t = np.concatenate([strip_t, far_t + len(strip_v)])
+    out = filter_mesh_components(_mesh(v, t), min_triangle_count=10)
+    ov, ot = out.vertex.positions.numpy(), out.triangle.indices.numpy()
+    assert len(ot) == 2 * n and len(ov) == len(strip_v) and ov[:, 0].max() < 50          # tetrahedron dropped
+    assert np.array_equal(out.vertex.normals.numpy(), -ov) and out.vertex.colors is not None   # attributes follow
+    assert np.array_equal(ov[ot], strip_v[strip_t])
+    # nothing reaches the threshold: the largest component survives alone
+    out = filter_mesh_components(_mesh(v, t), min_triangle_count=10_000)
+    assert len(out.triangle.indices) == 2 * n
+    assert "Returning largest component only" in capsys.readouterr().out
+    # degenerate, rotated-duplicate and opposite-winding triangles; duplicated vertices are welded
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [1, 0, 0], [2, 0, 0], [2, 1, 0]], np.float32)  # 4 == 1
+    t = np.array([[0, 1, 2], [1, 2, 0], [0, 2, 1], [2, 2, 3], [4, 5, 6]], np.int32)
+    out = filter_mesh_components(_mesh(v, t, with_attrs=False), min_triangle_count=1)
+    ot = out.triangle.indices.numpy().tolist()
+    assert ot == [[0, 1, 2], [0, 2, 1], [1, 4, 5]]          # rotation removed, reversed kept, (4,5,6) -> (1,4,5)
+    assert len(out.vertex.positions) == 6                   # welded; unreferenced vertex 3 stays (nothing was filtered)
+    # three triangles on one edge: the smallest one goes
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, -3, 0], [0, 0, 0.5]], np.float32)
+    t = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4]], np.int32)
+    out = filter_mesh_components(_mesh(v, t, with_attrs=False), min_triangle_count=1)
+    assert out.triangle.indices.numpy().tolist() == [[0, 1, 2], [1, 0, 3]]
+    # empty mesh is returned unchanged
+    empty = _mesh(np.zeros((0, 3)), np.zeros((0, 3)), with_attrs=False)
+    assert filter_mesh_components(empty) is empty
