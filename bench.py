@@ -409,7 +409,9 @@ def cpu_step(orc, cfg, sample):
         keys = g.touch(d, K[i], Ewc[i], cfg["depth_max"], cfg["trunc"])
         g.integrate(keys, d, K[i], Ewc[i], cfg["depth_max"], cfg["trunc"],
                     color=None if colors is None else colors[i], Kc=None if Kc is None else Kc[i])
-    g.extract_mesh(cfg["weight_thr"])
+    mesh = g.extract_mesh(cfg["weight_thr"])
+    if cfg["color"]:
+        g.vertex_colors(mesh[3])          # the GPU step extracts vertex colours too
     return g
 
 
