@@ -185,3 +185,29 @@ def test_filter_mesh_components_follows_open3d_legacy_semantics(capsys):
     # empty mesh is returned unchanged
     empty = _mesh(np.zeros((0, 3)), np.zeros((0, 3)), with_attrs=False)
     assert filter_mesh_components(empty) is empty
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints ONE JSON line with the
+    contract's keys; under torchrun only rank 0 works, the other ranks exit 0 silently."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-frames", "3", "--workload", "quest300_v20mm"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["config"]["workload"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
