@@ -17,7 +17,7 @@ def test_ghost_modes_agree_across_processes():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = 4 if n >= 4 else 2
+    world = 2                      # the configuration this script was validated with (2 x B200)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(HERE, "mp_ghost_modes.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
