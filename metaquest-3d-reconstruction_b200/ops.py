@@ -109,6 +109,34 @@ def integrate(dataset: DepthDataset, depth_data_io, side: Side, use_confidence_f
     return vbg
 
 
+def integrate_fragment_point_cloud(depth_data_io, frag_dataset: DepthDataset, side: Side, config):
+    """Drop-in for integrate_fragment_point_cloud (depth_optimization/refine_fragment_poses.py:14-58; SURVEY 8f
+    N4): one fragment's frames -> fresh VoxelBlockGrid -> point cloud.  Returns (side, PointCloud), or None when
+    the fragment yields no points or fails (the reference logs and skips such fragments; the ICP / pose-graph
+    consumers of the point clouds stay out of scope).  `config` is a FragmentPoseRefinementConfig."""
+    try:
+        vbg = integrate(dataset=frag_dataset, depth_data_io=depth_data_io, side=side,
+                        use_confidence_filtered_depth=config.use_confidence_filtered_depth,
+                        confidence_threshold=config.confidence_threshold,
+                        valid_count_threshold=config.valid_count_threshold, voxel_size=config.voxel_size,
+                        block_resolution=config.block_resolution, block_count=config.block_count,
+                        depth_max=config.depth_max, trunc_voxel_multiplier=config.trunc_voxel_multiplier,
+                        device=config.device, show_progress=False, desc=None, vbg_opt=None)
+        pcd = vbg.extract_point_cloud()
+        if pcd.point.positions.shape[0] == 0:
+            print(f"[Warning] Fragment point cloud for {side.name} is empty (no valid points). "
+                  f"Dataset has {len(frag_dataset.timestamps)} frames. "
+                  f"This may indicate insufficient depth data or overly strict filtering.")
+            return None
+        return side, pcd
+    except Exception as e:
+        n = len(frag_dataset.timestamps)
+        print(f"[Error] integrate_fragment_point_cloud failed for {side.name}: {e}")
+        print(f"[Error] Fragment dataset info: {n} frames, timestamps range: "
+              f"{frag_dataset.timestamps.min() if n > 0 else 'N/A'} - {frag_dataset.timestamps.max() if n > 0 else 'N/A'}")
+        return None
+
+
 def estimate_depth_confidences(depth_data_io, config, device="CUDA:0", save: bool = True) -> dict:
     """Drop-in for estimate_depth_confidences (estimate_depth_confidences.py:120-154): one K4 launch per
     side instead of a process pool.  Writes `<side>_depth_confidence/<ts>.npz` (keys confidence_map f64,

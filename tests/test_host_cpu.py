@@ -211,3 +211,45 @@ def test_bench_reference_arm_contract(tmp_path):
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_integrate_fragment_point_cloud_contract(monkeypatch, capsys):
+    """integrate_fragment_point_cloud (refine_fragment_poses.py:14-58): forwards the fragment config to integrate(),
+    returns (side, point cloud), and turns empty clouds / failures into None with the reference's messages."""
+    import torch
+    from types import SimpleNamespace
+    from mq3d_b200 import ops
+    from mq3d_b200.config import FragmentPoseRefinementConfig
+    from mq3d_b200.geometry import PointCloud
+    cfg = FragmentPoseRefinementConfig(device="CUDA:0", voxel_size=0.02, depth_max=2.5, trunc_voxel_multiplier=6.0)
+    ds = SimpleNamespace(timestamps=np.array([10, 20, 30]))
+    seen = {}
+
+    class FakeGrid:
+        def __init__(self, n):
+            self.n = n
+
+        def extract_point_cloud(self):
+            return PointCloud(torch.zeros((self.n, 3)), torch.zeros((self.n, 3)))
+
+    def fake_integrate(**kw):
+        seen.update(kw)
+        return FakeGrid(seen.pop("_points", 5))
+
+    monkeypatch.setattr(ops, "integrate", fake_integrate)
+    side, pcd = ops.integrate_fragment_point_cloud("io", ds, Side.RIGHT, cfg)
+    assert side == Side.RIGHT and pcd.point.positions.shape == (5, 3)
+    assert seen["voxel_size"] == 0.02 and seen["depth_max"] == 2.5 and seen["trunc_voxel_multiplier"] == 6.0
+    assert seen["block_count"] == 50_000 and seen["device"] == "CUDA:0" and seen["vbg_opt"] is None
+    assert seen["dataset"] is ds and seen["depth_data_io"] == "io" and seen["use_confidence_filtered_depth"] is True
+    monkeypatch.setattr(ops, "integrate", lambda **kw: FakeGrid(0))
+    assert ops.integrate_fragment_point_cloud("io", ds, Side.LEFT, cfg) is None
+    assert "is empty (no valid points)" in capsys.readouterr().out
+
+    def boom(**kw):
+        raise RuntimeError("No block is touched in TSDF volume")
+
+    monkeypatch.setattr(ops, "integrate", boom)
+    assert ops.integrate_fragment_point_cloud("io", ds, Side.LEFT, cfg) is None
+    out = capsys.readouterr().out
+    assert "integrate_fragment_point_cloud failed for LEFT" in out and "10 - 30" in out
