@@ -426,11 +426,3 @@ extern "C" int mq3d_scene_cast_rays(mq3d_scene *s, const float *rays_dev, int64_
     MQ3D_CUDA(cudaGetLastError());
     return MQ3D_OK;
 }
-
-// debug helper (not part of the public ABI): copy the first `max_nodes` BVH nodes to the host
-extern "C" int mq3d_scene_debug_nodes(mq3d_scene *s, void *out_host, int max_nodes) {
-    int n = (int)(s->n_tris > 1 ? s->n_tris - 1 : 0);
-    if (n > max_nodes) n = max_nodes;
-    MQ3D_CUDA(cudaMemcpy(out_host, s->nodes, sizeof(BvhNode) * n, cudaMemcpyDeviceToHost));
-    return n;
-}
