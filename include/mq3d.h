@@ -145,6 +145,7 @@ typedef struct {
     int64_t voxel_updates;     /* voxel visits that passed every reject (updated-voxel count) */
     double touch_ms;           /* device time of the K2 launches (CUDA events on `stream`) */
     double integrate_ms;       /* device time of the K3 launches (CUDA events on `stream`) */
+    int64_t slow_div_batches;  /* batches holding a depth in (0, 2^-75): integrated with the guarded division */
 } mq3d_seq_stats;
 
 /* Fused replacement of the whole per-frame loop of integrate() (o3d_utils.py:231-236):
@@ -153,7 +154,10 @@ typedef struct {
  * it are applied in frame order, which is bit-identical to the frame-sequential loop.
  * depth_dev: float32 [n_frames][H][W] linear (K1 output); frame_valid_dev: int32[n_frames] or
  * NULL; color_dev: uint8 [n_frames][CH][CW][3] or NULL; Kd/Kc: host double[n_frames][9];
- * E: host double[n_frames][16].  Synchronises. */
+ * E: host double[n_frames][16].  All batches are enqueued without intermediate host synchronisation
+ * (overflow of the pool / hash table is detected on the device; the call then grows the grid and resumes
+ * from the failing batch); synchronises once before returning.  A valid frame whose (unpartitioned) touch
+ * yields no block => MQ3D_ERR_NO_BLOCK_TOUCHED after the remaining frames were integrated. */
 int mq3d_integrate_sequence(mq3d_grid *g, const float *depth_dev, const int32_t *frame_valid_dev,
                             int n_frames, int width, int height, const uint8_t *color_dev,
                             int color_width, int color_height, const double *Kd, const double *Kc,

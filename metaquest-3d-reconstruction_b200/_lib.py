@@ -39,7 +39,8 @@ SYMBOLS = [
 class SeqStats(C.Structure):
     _fields_ = [("frames_integrated", C.c_int64), ("block_visits", C.c_int64),
                 ("blocks_loaded", C.c_int64), ("num_blocks", C.c_int64), ("batches", C.c_int64),
-                ("voxel_updates", C.c_int64), ("touch_ms", C.c_double), ("integrate_ms", C.c_double)]
+                ("voxel_updates", C.c_int64), ("touch_ms", C.c_double), ("integrate_ms", C.c_double),
+                ("slow_div_batches", C.c_int64)]
 
 
 class Mq3dError(RuntimeError):

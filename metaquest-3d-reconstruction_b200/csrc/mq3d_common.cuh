@@ -172,6 +172,20 @@ static inline void inverse_transformation(const double E[16], double P[16]) {
     }
 }
 
+// device-resident state of one mq3d_integrate_sequence call: batches are enqueued back to back without
+// host synchronisation; a batch whose touch overflows the pool / table (or meets a key outside the key
+// range) records itself here, every later kernel of the call then returns at once, and the host -- which
+// reads this once at the end -- grows the grid and resumes at that batch
+struct SeqState {
+    int fail_batch;           // -1, else the first batch that failed
+    int fail_flags;           // 1 key out of range, 2 hash table full, 4 pool / load factor exceeded
+    int first_empty_frame;    // INT_MAX, else lowest valid frame that touched no block on ANY rank's partition
+    int frames_integrated;    // valid frames that touched at least one block
+    int slow_div_batches;     // batches that held a depth in (0, 2^-75) and took the guarded division
+    int pad;
+    unsigned long long blocks_loaded;   // sum over batches of the listed slots (block residencies)
+};
+
 // per-frame parameters of the fused sequence path (device array)
 struct FrameParams {
     Camera touch;   // K + inverse pose, scale 1   (DepthTouch)
@@ -208,18 +222,19 @@ struct mq3d_grid {
     int *stamp;           // [table_size] batch serial of last touch
     int *slot_list;       // [table_size] slots touched in the current batch
     int *slot_sorted;     // [table_size] same, heavy-first (LPT order for the dynamic scheduler)
-    // colour scratch of the fused path: packed RGBX frames and per-frame depth->colour pixel LUTs
+    // colour scratch of the fused path: a batch's colour frames resampled onto the depth pixel grid
     uint32_t *rgbx;
     int64_t rgbx_px;
-    int *color_lut;
-    int64_t color_lut_size;
     float *depth_scratch;   // frames / depth_scale when depth_scale != 1
     int64_t depth_scratch_size;
     // validated fast division by the truncation constant
     float div_checked_trunc;
     int div_fast_ok;
     int batch_serial;
-    FrameParams *frame_params_dev;  // [MQ3D_MAX_BATCH]
+    FrameParams *frame_params_dev;  // [frame_params_cap] (>= MQ3D_MAX_BATCH): the whole sequence of a call
+    int64_t frame_params_cap;
+    SeqState *seq_dev, *seq_host;   // device state of the running sequence call / pinned mirror
+    int *frame_any_dev;             // [MQ3D_MAX_BATCH] frame touched some block (before the partition filter)
     int32_t *idx_scratch;  // per-frame integrate: block index per key
     int64_t idx_scratch_size;
     int *ghost_cnt_dev, *ghost_cnt_host;  // [64] per-destination ghost counts (device / pinned)
@@ -239,7 +254,6 @@ struct mq3d_grid {
     int32_t *mc_nb;       // [n][27]
     uint32_t *mc_emask;   // [n][384]
     uint16_t *mc_eprefix; // [n][384]
-    uint8_t *mc_cubes;    // [n][4096]
     int32_t *mc_counts;   // [n][2] vertices, triangles (or points)
     int64_t *mc_offsets;  // [n+1][2]
     int64_t mc_blocks;    // n the scratch was built for

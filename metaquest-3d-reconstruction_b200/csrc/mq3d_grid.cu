@@ -96,8 +96,11 @@ static void release_pool_ptr(mq3d_grid *g, void *p) {
         return;
     }
     if (g->n_retired == g->cap_retired) {
-        g->cap_retired = g->cap_retired ? 2 * g->cap_retired : 16;
-        g->retired = (void **)realloc(g->retired, sizeof(void *) * g->cap_retired);
+        const int cap = g->cap_retired ? 2 * g->cap_retired : 16;
+        void **r = (void **)realloc(g->retired, sizeof(void *) * cap);
+        if (!r) return;   // out of host memory: the old array stays mapped for the peers and is leaked
+        g->retired = r;
+        g->cap_retired = cap;
     }
     g->retired[g->n_retired++] = p;
 }
@@ -151,6 +154,10 @@ extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t 
             MQ3D_CUDA(cudaMalloc(&g->counter_dev, sizeof(int) * 8));
             MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * 8, st));
             MQ3D_CUDA(cudaMalloc(&g->frame_params_dev, sizeof(FrameParams) * MQ3D_MAX_BATCH));
+            g->frame_params_cap = MQ3D_MAX_BATCH;
+            MQ3D_CUDA(cudaMalloc(&g->seq_dev, sizeof(SeqState)));
+            MQ3D_CUDA(cudaMallocHost(&g->seq_host, sizeof(SeqState)));
+            MQ3D_CUDA(cudaMalloc(&g->frame_any_dev, sizeof(int) * MQ3D_MAX_BATCH));
             MQ3D_CUDA(cudaMallocHost(&g->pinned_host, sizeof(int) * 16));
             g->pinned_host64 = reinterpret_cast<int64_t *>(g->pinned_host + 8);
             MQ3D_CUDA(cudaMalloc(&g->frame_counts_dev, sizeof(int) * MQ3D_MAX_BATCH));
@@ -178,13 +185,11 @@ static void free_mc(mq3d_grid *g) {
     cudaFree(g->mc_nb);
     cudaFree(g->mc_emask);
     cudaFree(g->mc_eprefix);
-    cudaFree(g->mc_cubes);
     cudaFree(g->mc_counts);
     cudaFree(g->mc_offsets);
     g->mc_nb = nullptr;
     g->mc_emask = nullptr;
     g->mc_eprefix = nullptr;
-    g->mc_cubes = nullptr;
     g->mc_counts = nullptr;
     g->mc_offsets = nullptr;
     g->mc_alloc_blocks = 0;
@@ -210,8 +215,10 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->slot_sorted);
     cudaFree(g->depth_scratch);
     cudaFree(g->rgbx);
-    cudaFree(g->color_lut);
     cudaFree(g->frame_params_dev);
+    cudaFree(g->seq_dev);
+    cudaFree(g->frame_any_dev);
+    if (g->seq_host) cudaFreeHost(g->seq_host);
     cudaFree(g->idx_scratch);
     cudaFree(g->ghost_cnt_dev);
     mq3d_peer_state_free(g);

@@ -41,6 +41,21 @@ def tile_owner(bx: int, by: int, bz: int, world: int, tile_blocks: int = 8) -> i
     return _hash64(_pack(bx >> s, by >> s, bz >> s)) % world
 
 
+def tile_owner_np(keys: np.ndarray, world: int, tile_blocks: int = 8) -> np.ndarray:
+    """Vectorised tile_owner for int block keys [n,3] -> int64 [n]."""
+    s = np.uint64(tile_blocks.bit_length() - 1)
+    k = (np.asarray(keys, dtype=np.int64) >> np.int64(s)) + _BIAS
+    k = k.astype(np.uint64) & np.uint64(0xFFFFFFFF)
+    h = (k[:, 0] << np.uint64(42)) | (k[:, 1] << np.uint64(21)) | k[:, 2]
+    with np.errstate(over="ignore"):
+        h ^= h >> np.uint64(33)
+        h *= np.uint64(0xFF51AFD7ED558CCD)
+        h ^= h >> np.uint64(33)
+        h *= np.uint64(0xC4CEB9FE1A85EC53)
+        h ^= h >> np.uint64(33)
+    return ((h & np.uint64(0xFFFFFFFF)) % np.uint64(world)).astype(np.int64)
+
+
 def block_needed(bx: int, by: int, bz: int, rank: int, world: int, tile_blocks: int = 8) -> bool:
     """True when the block is owned by `rank` or lies in the one-block shell around an owned tile."""
     if world <= 1:

@@ -126,7 +126,8 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
             total = SequenceStats(total.frames_integrated + st.frames_integrated, total.block_visits + st.block_visits,
                                   total.blocks_loaded + st.blocks_loaded, st.num_blocks, total.batches + st.batches,
                                   total.voxel_updates + st.voxel_updates, total.touch_ms + st.touch_ms,
-                                  total.integrate_ms + st.integrate_ms)
+                                  total.integrate_ms + st.integrate_ms,
+                                  total.slow_div_batches + st.slow_div_batches)
     return total
 
 

@@ -10,7 +10,7 @@ from . import synth
 
 
 def _trace(origin: torch.Tensor, dirs: torch.Tensor):
-    """origin [3], dirs [...,3] (float64) -> (t [...], surface id [...])."""
+    """origin [...,3] (broadcastable against dirs), dirs [...,3] (float64) -> (t [...], surface id [...])."""
     rmin, rmax, sc, sr, bmin, bmax = (torch.as_tensor(np.asarray(a, dtype=np.float64), device=dirs.device)
                                       for a in synth._scene_o3d())
     inv = 1.0 / dirs
@@ -21,7 +21,7 @@ def _trace(origin: torch.Tensor, dirs: torch.Tensor):
     oc = origin - sc
     a = (dirs * dirs).sum(-1)
     b = 2.0 * (dirs * oc).sum(-1)
-    c = (oc * oc).sum() - sr * sr
+    c = (oc * oc).sum(-1) - sr * sr
     disc = b * b - 4 * a * c
     ts = torch.where(disc > 0, (-b - torch.sqrt(disc.clamp_min(0))) / (2 * a), torch.full_like(a, float("inf")))
     ts = torch.where(ts > 0, ts, torch.full_like(ts, float("inf")))
@@ -40,8 +40,10 @@ def _trace(origin: torch.Tensor, dirs: torch.Tensor):
 
 
 def render_depth(e_cw: np.ndarray, device, width=synth.DEPTH_W, height=synth.DEPTH_H, noise=0.005,
-                 dropout=0.02, seed=1234) -> torch.Tensor:
-    """Raw NDC depth float32 [F,H,W] on `device` for camera->world poses e_cw [F,4,4] (Open3D frame)."""
+                 dropout=0.02, seed=1234, first_frame: int = 0, out: torch.Tensor = None, chunk: int = 32) -> torch.Tensor:
+    """Raw NDC depth float32 [F,H,W] on `device` for camera->world poses e_cw [F,4,4] (Open3D frame).
+    Frame i draws its noise from a generator seeded with seed + first_frame + i, so any slice of a sequence
+    can be rendered on its own (ranks render disjoint slices of one capture)."""
     fx, fy, cx, cy = synth.depth_intrinsics(width, height)
     u = torch.arange(width, dtype=torch.float64, device=device)
     v = torch.arange(height, dtype=torch.float64, device=device)
@@ -49,17 +51,23 @@ def render_depth(e_cw: np.ndarray, device, width=synth.DEPTH_W, height=synth.DEP
     dy = ((v - cy) / fy)[:, None].expand(height, width)
     dirs_cam = torch.stack([dx, dy, torch.ones_like(dx)], dim=-1)
     gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    out = torch.empty((len(e_cw), height, width), dtype=torch.float32, device=device)
-    for i in range(len(e_cw)):
-        e = torch.as_tensor(e_cw[i].astype(np.float64), device=device)
-        z, _ = _trace(e[:3, 3], dirs_cam @ e[:3, :3].T)
-        if noise > 0:
-            z = z * (1.0 + noise * torch.randn(z.shape, generator=gen, device=device, dtype=torch.float64))
-        d = 1.0 - synth.NEAR / z
-        if dropout > 0:
-            d = torch.where(torch.rand(z.shape, generator=gen, device=device) < dropout, torch.ones_like(d), d)
-        out[i] = d.to(torch.float32)
+    n = len(e_cw)
+    if out is None:
+        out = torch.empty((n, height, width), dtype=torch.float32, device=device)
+    e_all = torch.as_tensor(np.asarray(e_cw, dtype=np.float64), device=device)
+    for i0 in range(0, n, chunk):
+        e = e_all[i0:i0 + chunk]
+        dirs = torch.einsum("hwk,bjk->bhwj", dirs_cam, e[:, :3, :3])
+        z, _ = _trace(e[:, None, None, :3, 3], dirs)
+        for j in range(z.shape[0]):
+            gen.manual_seed(seed + first_frame + i0 + j)
+            zj = z[j]
+            if noise > 0:
+                zj = zj * (1.0 + noise * torch.randn(zj.shape, generator=gen, device=device, dtype=torch.float64))
+            d = 1.0 - synth.NEAR / zj
+            if dropout > 0:
+                d = torch.where(torch.rand(zj.shape, generator=gen, device=device) < dropout, torch.ones_like(d), d)
+            out[i0 + j] = d.to(torch.float32)
     return out
 
 

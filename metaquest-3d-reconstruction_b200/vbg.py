@@ -92,6 +92,7 @@ class SequenceStats:
     voxel_updates: int
     touch_ms: float = 0.0
     integrate_ms: float = 0.0
+    slow_div_batches: int = 0
 
     @property
     def voxel_visits(self) -> int:
@@ -318,7 +319,7 @@ class VoxelBlockGrid:
                     _lib.darr(E), C.c_float(depth_scale), C.c_float(depth_max), C.c_float(trunc_voxel_multiplier),
                     int(batch_frames), C.byref(st), _stream()))
             return SequenceStats(st.frames_integrated, st.block_visits, st.blocks_loaded, st.num_blocks, st.batches,
-                                 st.voxel_updates, st.touch_ms, st.integrate_ms)
+                                 st.voxel_updates, st.touch_ms, st.integrate_ms, st.slow_div_batches)
         if colors is not None and self.has_color:
             if colors.dtype != torch.uint8 or colors.dim() != 4 or colors.shape[0] != F or colors.shape[3] != 3:
                 raise RuntimeError("colors must be uint8 [F,H,W,3]")
@@ -332,7 +333,7 @@ class VoxelBlockGrid:
                 _lib.darr(Kc), _lib.darr(E), C.c_float(depth_scale), C.c_float(depth_max),
                 C.c_float(trunc_voxel_multiplier), int(batch_frames), C.byref(st), _stream()))
         return SequenceStats(st.frames_integrated, st.block_visits, st.blocks_loaded, st.num_blocks, st.batches,
-                             st.voxel_updates, st.touch_ms, st.integrate_ms)
+                             st.voxel_updates, st.touch_ms, st.integrate_ms, st.slow_div_batches)
 
     # -- pool views / persistence -------------------------------------------------------------------
     def _pool_ptrs(self):

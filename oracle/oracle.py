@@ -40,6 +40,17 @@ def lib():
     return _lib
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle's parallel loops (explicit: OMP_NUM_THREADS from a launcher is ignored).
+    Returns the team size now in effect."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return int(lib().orc_get_max_threads())
+
+
+def get_max_threads() -> int:
+    return int(lib().orc_get_max_threads())
+
+
 def _p(a, t=None):
     if a is None:
         return None

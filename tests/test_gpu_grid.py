@@ -155,7 +155,8 @@ def test_save_load_roundtrip(cuda_device, oracle, tmp_path):
 @pytest.mark.parametrize("color", [False, True])
 def test_integrate_shapes_are_bit_identical(cuda_device, oracle, color, monkeypatch):
     """Every work-item shape of the fused kernel (MQ3D_INTEG_VARIANT: whole / half / quarter / eighth blocks,
-    different CTA sizes) produces the same bits and the same statistics."""
+    different CTA sizes, with and without the warp-level cull of all-rejected frames, 4 or 8 voxels per thread)
+    produces the same bits and the same statistics."""
     import mq3d_b200  # noqa: F401
     from mq3d_b200 import synth
     from mq3d_b200.vbg import VoxelBlockGrid
@@ -173,7 +174,7 @@ def test_integrate_shapes_are_bit_identical(cuda_device, oracle, color, monkeypa
                   color_intrinsics=np.tile(np.array([[f, 0, cw / 2.0], [0, f, ch / 2.0], [0, 0, 1.0]]), (n, 1, 1)))
     attrs = ("tsdf", "weight", "color") if color else ("tsdf", "weight")
     results = {}
-    for variant in ("0", "9", "8", "12", "1", "3"):
+    for variant in ("0", "9", "8", "12", "20", "21", "22"):
         monkeypatch.setenv("MQ3D_INTEG_VARIANT", variant)
         g = VoxelBlockGrid(attr_names=attrs, voxel_size=0.02, block_count=3000, device=cuda_device)
         st = g.integrate_sequence(lin, K, Ewc, 4.0, 10.0, batch_frames=5, **kw)
@@ -186,3 +187,59 @@ def test_integrate_shapes_are_bit_identical(cuda_device, oracle, color, monkeypa
             if a is not None:
                 assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
                                       b.view(np.uint32) if b.dtype == np.float32 else b), variant
+
+
+@pytest.mark.parametrize("pixel", [(8, 12), (9, 13)])      # on / off the stride-4 touch lattice
+def test_tiny_depth_takes_the_guarded_division(cuda_device, oracle, pixel):
+    """A depth in (0, 2^-75) makes |depth - z| < 2^-100 possible -- outside the validated range of the unguarded
+    fast division -- so the batch that holds it is integrated by the guarded instantiation (k_touch scans every
+    pixel of every valid frame).  Bits equal the oracle's either way; the other batches stay on the fast kernel."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    cap = capture(12)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    lin = _linear(oracle, cap)
+    lin[7, pixel[0], pixel[1]] = 1e-30
+    og = oracle.Grid(0.02)
+    oracle_integrate_sequence(oracle, og, lin, K, Ewc, DEPTH_MAX, TRUNC)
+    vbg = VoxelBlockGrid(voxel_size=0.02, block_count=1000, device=cuda_device)
+    st = vbg.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, DEPTH_MAX, TRUNC, batch_frames=4)
+    assert st.batches == 3 and st.slow_div_batches == 1
+    k0, t0, w0 = sort_blocks(*oracle_export(og))
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+
+
+def test_sequence_resumes_after_mid_sequence_growth(cuda_device, oracle):
+    """All batches of a call are enqueued without host synchronisation; a batch whose touch overflows the pool or
+    the hash table stops the device-side pipeline, the host grows the grid and resumes from that batch.  Start so
+    small that both the pool and the table overflow several times; a failed call (frame that touches nothing)
+    leaves no stale frame bits behind for the next call on the same grid."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    cap = capture(12)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    lin = _linear(oracle, cap)
+    og = oracle.Grid(0.01)
+    visits, updated = oracle_integrate_sequence(oracle, og, lin, K, Ewc, DEPTH_MAX, TRUNC)
+    vbg = VoxelBlockGrid(voxel_size=0.01, block_count=8, device=cuda_device)
+    cap0 = vbg.capacity()
+    st = vbg.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, DEPTH_MAX, TRUNC, batch_frames=2)
+    assert vbg.capacity() >= og.num_blocks > cap0
+    assert (st.frames_integrated, st.block_visits, st.voxel_updates, st.num_blocks) == (12, visits, updated, og.num_blocks)
+    k0, t0, w0 = sort_blocks(*oracle_export(og))
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    # error exit, then a clean call with another batch size on the same grid
+    bad = lin[:5].copy()
+    bad[3] = 0.0
+    g2 = VoxelBlockGrid(voxel_size=0.02, block_count=1000, device=cuda_device)
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        g2.integrate_sequence(torch.from_numpy(bad).to(cuda_device), K[:5], Ewc[:5], DEPTH_MAX, TRUNC, batch_frames=3)
+    g2.reset()
+    og2 = oracle.Grid(0.02)
+    oracle_integrate_sequence(oracle, og2, lin, K, Ewc, DEPTH_MAX, TRUNC)
+    g2.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, DEPTH_MAX, TRUNC, batch_frames=40)
+    k0, t0, w0 = sort_blocks(*oracle_export(og2))
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in g2.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))

@@ -179,3 +179,34 @@ def test_ghost_pull_from_peer_pools(cuda_device, oracle, world, tile, color):
                 assert np.array_equal(got[3][i].view(np.uint32), exp[3][j].view(np.uint32))
     with pytest.raises(Exception):
         grids[0].ghost_pull(descs[::-1].copy())          # descriptors out of rank order are rejected
+
+
+def test_frame_inside_other_ranks_blocks_is_not_an_empty_frame(cuda_device, oracle):
+    """Open3D's "No block is touched" is a property of the frame, not of a rank's partition: a close-up frame whose
+    frustum lies entirely in blocks owned by other ranks must not raise on the rank that owns none of them (it
+    would leave its peers alone in the following collectives), while a frame that touches nothing at all still
+    raises on every rank."""
+    from mq3d_b200.dist import tile_owner
+    from mq3d_b200.vbg import VoxelBlockGrid
+    H = W = 64
+    K = np.array([[[32.0, 0, 32.0], [0, 32.0, 32.0], [0, 0, 1.0]]], np.float32)
+    E = np.eye(4, dtype=np.float32)[None]
+    depth = np.zeros((1, H, W), np.float32)
+    depth[0, 28:36, 28:36] = 0.30           # a small patch straight ahead: a handful of blocks around z = 0.3 m
+    og = oracle.Grid(0.01)
+    keys = og.touch(depth[0], K[0], E[0], 1.5, 8.0)
+    world, tile = 8, 8                      # 1.28 m tiles: all touched blocks share one or two tiles
+    owners = {tile_owner(*map(int, k), world, tile) for k in keys}
+    idle = [r for r in range(world) if r not in owners]
+    assert idle and len(keys) > 0
+    d = torch.from_numpy(depth).to(cuda_device)
+    for rank in (idle[0], sorted(owners)[0]):
+        g = VoxelBlockGrid(voxel_size=0.01, block_count=500, device=cuda_device)
+        g.set_partition(rank, world, tile, integrate_ghosts=False)
+        st = g.integrate_sequence(d, K, E, 1.5, 8.0)
+        assert st.frames_integrated == 1
+        assert (st.num_blocks == 0) == (rank == idle[0])
+    g = VoxelBlockGrid(voxel_size=0.01, block_count=500, device=cuda_device)
+    g.set_partition(idle[0], world, tile, integrate_ghosts=False)
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        g.integrate_sequence(torch.zeros_like(d), K, E, 1.5, 8.0)

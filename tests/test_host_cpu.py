@@ -208,6 +208,14 @@ def test_bench_reference_arm_contract(tmp_path):
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["config"]["workload"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the arm's config is the GPU arm's (same keys and values), the bounded sample is described separately
+    assert d["config"]["frames"] == 300 and d["config"]["voxel_size"] == 0.02 and "3 of the 300 frames" in d["cpu_baseline"]["sample"]
+    # a launcher's OMP_NUM_THREADS=1 (torch.distributed.run exports it) must not shrink the OpenMP team
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d1 = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d1["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == d["cpu_baseline"]["cores"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
