@@ -721,7 +721,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames per side")
-    ap.add_argument("--batch", type=int, default=64, help="frames per block residency (<= 256)")
+    ap.add_argument("--batch", type=int, default=256, help="frames per block residency (<= 256)")
     ap.add_argument("--tile", type=int, default=1, help="partition super-tile edge in blocks (N > 1)")
     ap.add_argument("--ghosts", default="pull", choices=["pull", "exchange", "integrate"],
                     help="N > 1: 'integrate' = every rank also integrates its ghost shell (no exchange, the "

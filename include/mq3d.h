@@ -193,6 +193,14 @@ int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int64_t *n_ver
                             int64_t *n_triangles, void *stream);
 int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *normals_dev,
                            int32_t *triangles_dev, int32_t *vertex_keys_dev, void *stream);
+/* Single-call form of the pair above for callers that can bound the mesh size (e.g. from the previous extraction):
+ * classification, scan and emission are enqueued back to back without a host round trip; the kernels read the
+ * totals on the device and write nothing when the mesh exceeds cap_vertices / cap_triangles.  Synchronises once,
+ * returns the true sizes; if they exceed the capacities the caller allocates exact buffers and calls
+ * mq3d_extract_mesh_fill (and _colors) -- the classification is kept.  vertex_keys_dev / colors_dev may be NULL. */
+int mq3d_extract_mesh(mq3d_grid *g, float weight_threshold, float *vertices_dev, float *normals_dev,
+                      int32_t *triangles_dev, int32_t *vertex_keys_dev, float *colors_dev, int64_t cap_vertices,
+                      int64_t cap_triangles, int64_t *n_vertices, int64_t *n_triangles, void *stream);
 int mq3d_extract_points_count(mq3d_grid *g, float weight_threshold, int64_t *n_points, void *stream);
 int mq3d_extract_points_fill(mq3d_grid *g, float *points_dev, float *normals_dev,
                              int32_t *point_keys_dev, void *stream);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mq3d_grid_ghost_counts", "mq3d_grid_peer_descriptor", "mq3d_grid_ghost_pull",
     "mq3d_depth_prepare", "mq3d_touch", "mq3d_integrate", "mq3d_integrate_sequence",
     "mq3d_color_resample", "mq3d_integrate_sequence_rgbx",
-    "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_points_count",
+    "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_mesh", "mq3d_extract_points_count",
     "mq3d_extract_points_fill", "mq3d_extract_mesh_colors", "mq3d_extract_points_colors", "mq3d_confidence",
     "mq3d_scene_create", "mq3d_scene_destroy", "mq3d_scene_add_triangles",
     "mq3d_scene_create_rays_pinhole", "mq3d_scene_cast_rays",
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
                                          C.POINTER(SeqStats), vp],
         "mq3d_extract_mesh_count": [vp, f32, C.POINTER(i64), C.POINTER(i64), vp],
         "mq3d_extract_mesh_fill": [vp, vp, vp, vp, vp, vp],
+        "mq3d_extract_mesh": [vp, f32, vp, vp, vp, vp, vp, i64, i64, C.POINTER(i64), C.POINTER(i64), vp],
         "mq3d_extract_points_count": [vp, f32, C.POINTER(i64), vp],
         "mq3d_extract_points_fill": [vp, vp, vp, vp, vp],
         "mq3d_extract_mesh_colors": [vp, vp, vp],

@@ -11,6 +11,7 @@
 #define MQ3D_RES 16
 #define MQ3D_RES3 4096
 #define MQ3D_MAX_BATCH 256
+#define MQ3D_COUNTER_WORDS 1024
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -215,12 +216,12 @@ struct mq3d_grid {
     // per-frame touch scratch ("frustum hashmap")
     HashView frustum;
     int64_t frustum_size;
-    int *counter_dev;     // small int scratch [8]
+    int *counter_dev;     // int scratch [MQ3D_COUNTER_WORDS]: counters of touch / list / sort / integrate, misc flags
     // fused-sequence scratch (indexed by hash slot)
     uint32_t *bitmap;     // [table_size][bitmap_words]
     int bitmap_words;
-    int *stamp;           // [table_size] batch serial of last touch
     int *slot_list;       // [table_size] slots touched in the current batch
+    uint16_t *slot_cnt;   // [table_size] number of frames of the batch that touched the listed slot
     int *slot_sorted;     // [table_size] same, heavy-first (LPT order for the dynamic scheduler)
     // colour scratch of the fused path: a batch's colour frames resampled onto the depth pixel grid
     uint32_t *rgbx;
@@ -230,7 +231,6 @@ struct mq3d_grid {
     // validated fast division by the truncation constant
     float div_checked_trunc;
     int div_fast_ok;
-    int batch_serial;
     FrameParams *frame_params_dev;  // [frame_params_cap] (>= MQ3D_MAX_BATCH): the whole sequence of a call
     int64_t frame_params_cap;
     SeqState *seq_dev, *seq_host;   // device state of the running sequence call / pinned mirror
@@ -256,6 +256,7 @@ struct mq3d_grid {
     uint16_t *mc_eprefix; // [n][384]
     int32_t *mc_counts;   // [n][2] vertices, triangles (or points)
     int64_t *mc_offsets;  // [n+1][2]
+    long long *mc_totals; // [chunks][2] partial sums of the count scan
     int64_t mc_blocks;    // n the scratch was built for
     int64_t mc_alloc_blocks;
     int mc_state;         // 0 none, 1 mesh counted, 2 points counted

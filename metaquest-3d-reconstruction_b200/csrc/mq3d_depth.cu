@@ -21,26 +21,45 @@ __device__ __forceinline__ unsigned validity_bits(float v) {
     return (v != 0.0f ? 1u : 0u) | (v != 1.0f ? 2u : 0u) | (isnan(v) ? 4u : 0u) | (!(v >= 0.0f) ? 8u : 0u);
 }
 
+// The per-frame conversion constants travel by value with the launch (constant bank), K1_GROUP frames per
+// launch: no device-side parameter scratch, hence no state shared between callers, streams or threads.
+#define K1_GROUP 512
+struct NdcGroup {
+    NdcParams p[K1_GROUP];   // 12 KB
+};
+
+// One CTA covers K1_UNROLL * 256 float4 of one frame: every thread has its loads in flight before the first
+// float64 division starts (the divisions, ~1.1 ms of FP64 pipe time for 10^4 frames, then overlap the stream).
+#define K1_UNROLL 4
 template <bool MASK>
 __global__ void __launch_bounds__(256)
-k_depth_prepare(const float *__restrict__ raw, int64_t px_per_frame, const NdcParams *__restrict__ params,
+k_depth_prepare(const float *__restrict__ raw, int64_t px_per_frame, const __grid_constant__ NdcGroup params, int frame0,
                 const double *__restrict__ conf, const int32_t *__restrict__ count,
                 const uint8_t *__restrict__ has_conf, double conf_thr, int32_t count_thr,
                 float *__restrict__ out, int32_t *__restrict__ frame_bits) {
-    int f = blockIdx.y;
-    NdcParams p = params[f];
-    int64_t base = (int64_t)f * px_per_frame;
-    int64_t n4 = px_per_frame >> 2;
-    bool mask = MASK && (has_conf == nullptr || has_conf[f]);
+    const int f = frame0 + blockIdx.y;
+    const NdcParams p = params.p[blockIdx.y];
+    const int64_t base = (int64_t)f * px_per_frame;
+    const int64_t n4 = px_per_frame >> 2;
+    const bool mask = MASK && (has_conf == nullptr || has_conf[f]);
     unsigned bits = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 r = __ldg(reinterpret_cast<const float4 *>(raw + base) + i);
-        bits |= validity_bits(r.x) | validity_bits(r.y) | validity_bits(r.z) | validity_bits(r.w);
+    const int64_t i0 = (int64_t)blockIdx.x * (256 * K1_UNROLL) + threadIdx.x;
+    float4 r[K1_UNROLL];
+#pragma unroll
+    for (int q = 0; q < K1_UNROLL; ++q) {
+        const int64_t i = i0 + 256 * q;
+        r[q] = i < n4 ? __ldcs(reinterpret_cast<const float4 *>(raw + base) + i) : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    }
+#pragma unroll
+    for (int q = 0; q < K1_UNROLL; ++q) {
+        const int64_t i = i0 + 256 * q;
+        if (i >= n4) continue;
+        bits |= validity_bits(r[q].x) | validity_bits(r[q].y) | validity_bits(r[q].z) | validity_bits(r[q].w);
         float4 o;
-        o.x = ndc_to_linear(r.x, p);
-        o.y = ndc_to_linear(r.y, p);
-        o.z = ndc_to_linear(r.z, p);
-        o.w = ndc_to_linear(r.w, p);
+        o.x = ndc_to_linear(r[q].x, p);
+        o.y = ndc_to_linear(r[q].y, p);
+        o.z = ndc_to_linear(r[q].z, p);
+        o.w = ndc_to_linear(r[q].w, p);
         if (mask) {
             const double2 *c2 = reinterpret_cast<const double2 *>(conf + base) + 2 * i;
             double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1);
@@ -52,14 +71,15 @@ k_depth_prepare(const float *__restrict__ raw, int64_t px_per_frame, const NdcPa
         }
         reinterpret_cast<float4 *>(out + base)[i] = o;
     }
-    // scalar tail (px_per_frame not a multiple of 4)
-    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_frame;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float r = raw[base + i];
-        bits |= validity_bits(r);
-        float o = ndc_to_linear(r, p);
-        if (mask && (conf[base + i] < conf_thr || count[base + i] < count_thr)) o = 0.0f;
-        out[base + i] = o;
+    // scalar tail (px_per_frame not a multiple of 4): first CTA of the frame
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < px_per_frame; i += blockDim.x) {
+            float v = raw[base + i];
+            bits |= validity_bits(v);
+            float o = ndc_to_linear(v, p);
+            if (mask && (conf[base + i] < conf_thr || count[base + i] < count_thr)) o = 0.0f;
+            out[base + i] = o;
+        }
     }
     bits = __reduce_or_sync(0xFFFFFFFFu, bits);
     if ((threadIdx.x & 31) == 0 && bits) atomicOr(&frame_bits[f], (int)bits);
@@ -80,7 +100,6 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
     MQ3D_REQUIRE(n_frames > 0 && width > 0 && height > 0, "empty input");
     MQ3D_REQUIRE((conf_dev == nullptr) == (count_dev == nullptr), "conf and count must be given together");
     int64_t px = (int64_t)width * height;
-    MQ3D_REQUIRE(n_frames <= 65535, "at most 65535 frames per call");
     cudaStream_t st = as_stream(stream);
     NdcParams *hp = (NdcParams *)malloc(sizeof(NdcParams) * n_frames);
     for (int i = 0; i < n_frames; ++i) {
@@ -96,22 +115,7 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
         }
         hp[i].pad = 0;
     }
-    // per-device parameter scratch, kept across calls (one stream per device by contract)
-    static NdcParams *s_dp[64] = {nullptr};
-    static int s_dp_cap[64] = {0};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && dev < 64 && n_frames > s_dp_cap[dev]) {
-        cudaFree(s_dp[dev]);
-        s_dp[dev] = nullptr;
-        s_dp_cap[dev] = 0;
-        e = cudaMalloc(&s_dp[dev], sizeof(NdcParams) * n_frames);
-        if (e == cudaSuccess) s_dp_cap[dev] = n_frames;
-    }
-    NdcParams *dp = (e == cudaSuccess && dev < 64) ? s_dp[dev] : nullptr;
-    if (e == cudaSuccess && dp == nullptr) e = cudaErrorInvalidDevice;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dp, hp, sizeof(NdcParams) * n_frames, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(frame_valid_dev, 0, sizeof(int32_t) * n_frames, st);
+    cudaError_t e = cudaMemsetAsync(frame_valid_dev, 0, sizeof(int32_t) * n_frames, st);
     if (e == cudaSuccess) {
         // alignment: float4 path needs 16-B aligned frame bases
         bool aligned = ((px & 3) == 0) && (((uintptr_t)raw_dev | (uintptr_t)out_dev) & 15) == 0 &&
@@ -121,19 +125,30 @@ extern "C" int mq3d_depth_prepare(const float *raw_dev, int n_frames, int width,
             mq3d_set_error("depth_prepare: buffers must be 16-byte aligned and W*H a multiple of 4");
             return MQ3D_ERR_INVALID;
         }
-        int bx = (int)((px / 4 + 255) / 256);
-        if (bx > 148 * 4) bx = 148 * 4;
-        dim3 grid(bx, n_frames);
-        if (conf_dev)
-            k_depth_prepare<true><<<grid, 256, 0, st>>>(raw_dev, px, dp, conf_dev, count_dev, has_conf_dev, conf_thr,
-                                                        count_thr, out_dev, frame_valid_dev);
-        else
-            k_depth_prepare<false><<<grid, 256, 0, st>>>(raw_dev, px, dp, nullptr, nullptr, nullptr, 0.0, 0, out_dev,
-                                                         frame_valid_dev);
+        int bx = (int)((px / 4 + 256 * K1_UNROLL - 1) / (256 * K1_UNROLL));
+        if (bx < 1) bx = 1;
+        NdcGroup *grp = (NdcGroup *)calloc(1, sizeof(NdcGroup));
+        if (!grp) {
+            free(hp);
+            mq3d_set_error("out of host memory");
+            return MQ3D_ERR_INVALID;
+        }
+        for (int f0 = 0; f0 < n_frames; f0 += K1_GROUP) {
+            const int nf = n_frames - f0 < K1_GROUP ? n_frames - f0 : K1_GROUP;
+            memcpy(grp->p, hp + f0, sizeof(NdcParams) * nf);
+            dim3 grid(bx, nf);
+            if (conf_dev)
+                k_depth_prepare<true><<<grid, 256, 0, st>>>(raw_dev, px, *grp, f0, conf_dev, count_dev, has_conf_dev,
+                                                            conf_thr, count_thr, out_dev, frame_valid_dev);
+            else
+                k_depth_prepare<false><<<grid, 256, 0, st>>>(raw_dev, px, *grp, f0, nullptr, nullptr, nullptr, 0.0, 0,
+                                                             out_dev, frame_valid_dev);
+        }
+        free(grp);
         k_depth_finalize<<<(n_frames + 255) / 256, 256, 0, st>>>(frame_valid_dev, n_frames);
         e = cudaGetLastError();
     }
-    free(hp);  // pageable H2D copies are staged before cudaMemcpyAsync returns
+    free(hp);
     if (e != cudaSuccess) {
         mq3d_set_error("depth_prepare: %s", cudaGetErrorString(e));
         return MQ3D_ERR_CUDA;

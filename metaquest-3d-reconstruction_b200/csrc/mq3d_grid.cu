@@ -74,17 +74,17 @@ static int alloc_table(HashView *h, int64_t size, cudaStream_t st) {
 
 static int alloc_slot_scratch(mq3d_grid *g, cudaStream_t st) {
     if (g->bitmap) cudaFree(g->bitmap);
-    if (g->stamp) cudaFree(g->stamp);
+    if (g->slot_cnt) cudaFree(g->slot_cnt);
     if (g->slot_list) cudaFree(g->slot_list);
     if (g->slot_sorted) cudaFree(g->slot_sorted);
     g->slot_sorted = nullptr;
     MQ3D_CUDA(cudaMalloc(&g->slot_sorted, sizeof(int) * g->table_size));
     g->bitmap_words = MQ3D_MAX_BATCH / 32;
     MQ3D_CUDA(cudaMalloc(&g->bitmap, sizeof(uint32_t) * g->table_size * g->bitmap_words));
-    MQ3D_CUDA(cudaMalloc(&g->stamp, sizeof(int) * g->table_size));
+    g->slot_cnt = nullptr;
+    MQ3D_CUDA(cudaMalloc(&g->slot_cnt, sizeof(uint16_t) * g->table_size));
     MQ3D_CUDA(cudaMalloc(&g->slot_list, sizeof(int) * g->table_size));
     MQ3D_CUDA(cudaMemsetAsync(g->bitmap, 0, sizeof(uint32_t) * g->table_size * g->bitmap_words, st));
-    MQ3D_CUDA(cudaMemsetAsync(g->stamp, 0, sizeof(int) * g->table_size, st));
     return MQ3D_OK;
 }
 
@@ -151,8 +151,8 @@ extern "C" int mq3d_grid_create(float voxel_size, int block_resolution, int64_t 
             if (g->color) MQ3D_CUDA(cudaMemsetAsync(g->color, 0, sizeof(float) * 3 * MQ3D_RES3 * g->capacity, st));
             MQ3D_CUDA(cudaMalloc(&g->n_blocks_dev, sizeof(int)));
             MQ3D_CUDA(cudaMemsetAsync(g->n_blocks_dev, 0, sizeof(int), st));
-            MQ3D_CUDA(cudaMalloc(&g->counter_dev, sizeof(int) * 8));
-            MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * 8, st));
+            MQ3D_CUDA(cudaMalloc(&g->counter_dev, sizeof(int) * MQ3D_COUNTER_WORDS));
+            MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int) * MQ3D_COUNTER_WORDS, st));
             MQ3D_CUDA(cudaMalloc(&g->frame_params_dev, sizeof(FrameParams) * MQ3D_MAX_BATCH));
             g->frame_params_cap = MQ3D_MAX_BATCH;
             MQ3D_CUDA(cudaMalloc(&g->seq_dev, sizeof(SeqState)));
@@ -187,11 +187,13 @@ static void free_mc(mq3d_grid *g) {
     cudaFree(g->mc_eprefix);
     cudaFree(g->mc_counts);
     cudaFree(g->mc_offsets);
+    cudaFree(g->mc_totals);
     g->mc_nb = nullptr;
     g->mc_emask = nullptr;
     g->mc_eprefix = nullptr;
     g->mc_counts = nullptr;
     g->mc_offsets = nullptr;
+    g->mc_totals = nullptr;
     g->mc_alloc_blocks = 0;
     g->mc_state = 0;
 }
@@ -210,7 +212,7 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->n_blocks_dev);
     cudaFree(g->counter_dev);
     cudaFree(g->bitmap);
-    cudaFree(g->stamp);
+    cudaFree(g->slot_cnt);
     cudaFree(g->slot_list);
     cudaFree(g->slot_sorted);
     cudaFree(g->depth_scratch);
@@ -483,10 +485,8 @@ extern "C" int mq3d_grid_reset(mq3d_grid *g, void *stream) {
     if (g->color) MQ3D_CUDA(cudaMemsetAsync(g->color, 0, sizeof(float) * 3 * MQ3D_RES3 * live, st));
     MQ3D_CUDA(cudaMemsetAsync(g->n_blocks_dev, 0, sizeof(int), st));
     MQ3D_CUDA(cudaMemsetAsync(g->bitmap, 0, sizeof(uint32_t) * g->table_size * g->bitmap_words, st));
-    MQ3D_CUDA(cudaMemsetAsync(g->stamp, 0, sizeof(int) * g->table_size, st));
     MQ3D_CUDA(cudaStreamSynchronize(st));
     g->n_blocks_host = 0;
-    g->batch_serial = 0;
     g->mc_state = 0;
     return MQ3D_OK;
 }

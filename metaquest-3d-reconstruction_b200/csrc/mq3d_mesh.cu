@@ -98,8 +98,10 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
     __shared__ unsigned s_valid[SROW_WORDS], s_sign[SROW_WORDS];
     __shared__ unsigned s_cok[17 * 17];
     __shared__ int s_wtot[8][5];
+    __shared__ unsigned char s_tc[256];      // triangles per cube case (constant-bank reads with a per-lane index serialise)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
+    if (tid < 256) s_tc[tid] = (unsigned char)(__ldg(&MC_TRI_PACKED[tid]) >> 60);   // read in phase C, two barriers later
     {
         // ---- phase A: one thread per (y,z) row of the (-1..16)^2 neighbourhood: the 16 interior voxels as
         // four float4 of tsdf and of weight, the x=-1 / x=16 columns as scalars from the -x / +x neighbour
@@ -173,7 +175,7 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
         const unsigned flat = same4 & (same4 >> 1) & ~(s00 ^ (s00 >> 1));
         const unsigned surf = (c00 & ~flat) >> 1 & 0xFFFFu;
         int ntri = 0;
-        for (unsigned m = surf; m; m &= m - 1) ntri += MC_TRI_COUNT[cube_case(s00, s10, s01, s11, __ffs(m))];
+        for (unsigned m = surf; m; m &= m - 1) ntri += s_tc[cube_case(s00, s10, s01, s11, __ffs(m))];
         uint16_t *r16 = rows16 + b * R16_WORDS;
         r16[R16_EMASK + tid] = (uint16_t)mx;
         r16[R16_EMASK + 256 + tid] = (uint16_t)my;
@@ -224,63 +226,101 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// scan of per-block (a, b) counts -> int64 exclusive offsets [n+1][2]
+// scan of per-block (a, b) counts -> int64 exclusive offsets [n+1][2]: k_scan_totals sums chunks of
+// SCAN_CHUNK blocks, k_scan_counts adds the totals of the preceding chunks (a few dozen values) to a local
+// scan of its own chunk.  Deterministic, no inter-CTA waiting.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t *__restrict__ counts, int64_t n, int64_t *__restrict__ offsets) {
-    __shared__ long long s_a[32], s_b[32];
+#define SCAN_THREADS 256
+#define SCAN_PER 8
+#define SCAN_CHUNK (SCAN_THREADS * SCAN_PER)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_totals(const int32_t *__restrict__ counts, int64_t n, long long *__restrict__ totals) {
+    __shared__ long long s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long a = 0, c = 0;
+    for (int q = 0; q < SCAN_PER; ++q) {
+        const int64_t i = (int64_t)blockIdx.x * SCAN_CHUNK + q * SCAN_THREADS + tid;
+        if (i < n) {
+            const int2 v = __ldg(reinterpret_cast<const int2 *>(counts) + i);
+            a += v.x;
+            c += v.y;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    }
+    if (lane == 0) { s_a[warp] = a; s_b[warp] = c; }
+    __syncthreads();
+    if (tid == 0) {
+        long long ta = 0, tb = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+        totals[2 * blockIdx.x] = ta;
+        totals[2 * blockIdx.x + 1] = tb;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_counts(const int32_t *__restrict__ counts, int64_t n, const long long *__restrict__ totals,
+                                                              int64_t *__restrict__ offsets) {
+    __shared__ long long s_a[SCAN_THREADS / 32], s_b[SCAN_THREADS / 32];
     __shared__ long long s_carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry[0] = s_carry[1] = 0;
-    __syncthreads();
-    constexpr int PER = 8;   // consecutive blocks per thread: 8192 blocks per sweep
-    for (int64_t base = 0; base < n; base += 1024 * PER) {
-        const int64_t i0 = base + (int64_t)tid * PER;
+    // carry-in: totals of the preceding chunks
+    {
         long long a = 0, c = 0;
-        long long la[PER], lc[PER];
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const int64_t i = i0 + q;
-            la[q] = a;
-            lc[q] = c;
-            if (i < n) {
-                const int2 v = __ldg(reinterpret_cast<const int2 *>(counts) + i);
-                a += v.x;
-                c += v.y;
-            }
+        for (int i = tid; i < (int)blockIdx.x; i += SCAN_THREADS) { a += totals[2 * i]; c += totals[2 * i + 1]; }
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
         }
-        long long ia = a, ic = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            long long ta = __shfl_up_sync(0xFFFFFFFFu, ia, o), tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
-            if (lane >= o) { ia += ta; ic += tc; }
-        }
-        if (lane == 31) { s_a[warp] = ia; s_b[warp] = ic; }
+        if (lane == 0) { s_a[warp] = a; s_b[warp] = c; }
         __syncthreads();
-        if (warp == 0) {
-            long long wa = s_a[lane], wb = s_b[lane];
-            long long xa = wa, xb = wb;
-            for (int o = 1; o < 32; o <<= 1) {
-                long long ta = __shfl_up_sync(0xFFFFFFFFu, xa, o), tb = __shfl_up_sync(0xFFFFFFFFu, xb, o);
-                if (lane >= o) { xa += ta; xb += tb; }
-            }
-            s_a[lane] = xa - wa;
-            s_b[lane] = xb - wb;
+        if (tid == 0) {
+            long long ta = 0, tb = 0;
+            for (int w = 0; w < SCAN_THREADS / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+            s_carry[0] = ta;
+            s_carry[1] = tb;
         }
-        __syncthreads();
-        long long ca = s_carry[0], cb = s_carry[1];
-        const long long ta = ca + s_a[warp] + ia - a, tb = cb + s_b[warp] + ic - c;   // exclusive prefix of this thread
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const int64_t i = i0 + q;
-            if (i < n) {
-                offsets[2 * i] = ta + la[q];
-                offsets[2 * i + 1] = tb + lc[q];
-            }
-        }
-        __syncthreads();
-        if (tid == 1023) { s_carry[0] = ca + s_a[warp] + ia; s_carry[1] = cb + s_b[warp] + ic; }
         __syncthreads();
     }
-    if (tid == 0) { offsets[2 * n] = s_carry[0]; offsets[2 * n + 1] = s_carry[1]; }
+    // SCAN_PER consecutive blocks per thread
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)tid * SCAN_PER;
+    long long a = 0, c = 0, la[SCAN_PER], lc[SCAN_PER];
+#pragma unroll
+    for (int q = 0; q < SCAN_PER; ++q) {
+        la[q] = a;
+        lc[q] = c;
+        if (i0 + q < n) {
+            const int2 v = __ldg(reinterpret_cast<const int2 *>(counts) + i0 + q);
+            a += v.x;
+            c += v.y;
+        }
+    }
+    long long ia = a, ic = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long ta = __shfl_up_sync(0xFFFFFFFFu, ia, o), tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+        if (lane >= o) { ia += ta; ic += tc; }
+    }
+    __syncthreads();
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ic; }
+    __syncthreads();
+    long long wa = 0, wb = 0, ta = 0, tb = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) { wa += s_a[w]; wb += s_b[w]; }
+        ta += s_a[w];
+        tb += s_b[w];
+    }
+    const long long pa = s_carry[0] + wa + ia - a, pb = s_carry[1] + wb + ic - c;   // exclusive prefix of this thread
+#pragma unroll
+    for (int q = 0; q < SCAN_PER; ++q) {
+        if (i0 + q < n) {
+            offsets[2 * (i0 + q)] = pa + la[q];
+            offsets[2 * (i0 + q) + 1] = pb + lc[q];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        offsets[2 * n] = s_carry[0] + ta;
+        offsets[2 * n + 1] = s_carry[1] + tb;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,25 +381,32 @@ __device__ __forceinline__ void write_color(float *__restrict__ out, int64_t id,
                                     255.0f);
 }
 
-// vertex colours of the mesh laid out by k_mc_classify / k_scan_counts (same vertex order as k_mc_emit)
-__global__ void __launch_bounds__(256)
+// A block carries ~100 vertices and ~100 surface cubes on real surfaces: the emit kernels use EMIT_THREADS = 64
+// threads per block (two warps), so that most lanes have work and the per-warp instruction stream is paid twice
+// rather than eight times per block.
+#define EMIT_THREADS 64
+
+// vertex colours of the mesh laid out by k_mc_classify / k_scan_counts (same vertex order as k_mc_emit).
+// cap_v >= 0: do nothing if the mesh does not fit the caller's buffers (single-call extraction).
+__global__ void __launch_bounds__(EMIT_THREADS)
 k_mc_colors(const float *__restrict__ tsdf, const float *__restrict__ color, const int32_t *__restrict__ nb,
             const uint16_t *__restrict__ rows16, const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-            float *__restrict__ vcolors) {
+            float *__restrict__ vcolors, int64_t n_blocks, int64_t cap_v, int64_t cap_t) {
     __shared__ int s_nb[27];
     __shared__ uint16_t s_ep[768], s_em[768];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
+    if (cap_v >= 0 && (offsets[2 * n_blocks] > cap_v || offsets[2 * n_blocks + 1] > cap_t)) return;
     const int nv = counts[2 * b];
     if (nv == 0) return;
     if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
-    for (int i = tid; i < 768; i += 256) {
+    for (int i = tid; i < 768; i += EMIT_THREADS) {
         s_ep[i] = rows16[b * R16_WORDS + R16_EPREF + i];
         s_em[i] = rows16[b * R16_WORDS + R16_EMASK + i];
     }
     __syncthreads();
     const int64_t voff = offsets[2 * b];
-    for (int j = tid; j < nv; j += 256) {
+    for (int j = tid; j < nv; j += EMIT_THREADS) {
         int lo = 0, hi = 767;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -378,36 +425,35 @@ k_mc_colors(const float *__restrict__ tsdf, const float *__restrict__ color, con
 // ------------------------------------------------------------------------------------------------
 // emit
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// cap_v >= 0: do nothing if the mesh does not fit the caller's buffers (single-call extraction: the totals sit
+// at the end of the scanned offsets, the host learns them afterwards and retries with exact sizes).
+__global__ void __launch_bounds__(EMIT_THREADS)
 k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys, const int32_t *__restrict__ nb,
           const uint32_t *__restrict__ srow, const uint16_t *__restrict__ rows16, const int32_t *__restrict__ counts,
           const int64_t *__restrict__ offsets, float vs, float *__restrict__ verts, float *__restrict__ normals,
-          int32_t *__restrict__ tris, int32_t *__restrict__ vkeys) {
+          int32_t *__restrict__ tris, int32_t *__restrict__ vkeys, int64_t n_blocks, int64_t cap_v, int64_t cap_t) {
     __shared__ int s_nb[27];
     __shared__ __align__(16) uint16_t s_r16[R16_WORDS];
     __shared__ unsigned s_sign[SROW_WORDS];
-    __shared__ signed char s_tt[256 * 16];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
+    if (cap_v >= 0 && (offsets[2 * n_blocks] > cap_v || offsets[2 * n_blocks + 1] > cap_t)) return;
     const int nv = counts[2 * b], nt = counts[2 * b + 1];
     if (nv == 0 && nt == 0) return;
     if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(rows16 + b * R16_WORDS);
-        reinterpret_cast<uint4 *>(s_r16)[tid] = __ldg(src + tid);       // 288 x 16 B = 4.5 KB
-        if (tid < R16_WORDS / 8 - 256) reinterpret_cast<uint4 *>(s_r16)[256 + tid] = __ldg(src + 256 + tid);
+        for (int i = tid; i < R16_WORDS / 8; i += EMIT_THREADS) reinterpret_cast<uint4 *>(s_r16)[i] = __ldg(src + i);   // 4.5 KB
     }
     const bool do_tris = nt > 0 && tris != nullptr;
-    if (do_tris) {
-        for (int i = tid; i < SROW_WORDS; i += 256) s_sign[i] = srow[b * SROW_WORDS + i];
-        for (int i = tid; i < 256 * 16; i += 256) s_tt[i] = MC_TRI_TABLE[i >> 4][i & 15];
-    }
+    if (do_tris)
+        for (int i = tid; i < SROW_WORDS; i += EMIT_THREADS) s_sign[i] = srow[b * SROW_WORDS + i];
     __syncthreads();
     const int kx = block_keys[3 * b], ky = block_keys[3 * b + 1], kz = block_keys[3 * b + 2];
     const int64_t voff = offsets[2 * b], toff = offsets[2 * b + 1];
     // ---- vertices: one thread per vertex; (axis,row) by binary search in the prefix table, x = k-th set bit ----
     if (nv > 0) {
-        for (int j = tid; j < nv; j += 256) {
+        for (int j = tid; j < nv; j += EMIT_THREADS) {
             int lo = 0, hi = 767;                      // largest item with prefix <= j and a non-empty mask
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
@@ -439,7 +485,7 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
     if (do_tris) {
         const uint16_t *s_sp = s_r16 + R16_SPREF;      // no barrier between the vertex and the triangle phase
         const int ncubes = (int)s_sp[255] + __popc((unsigned)s_r16[R16_SURF + 255]);
-        for (int j = tid; j < ncubes; j += 256) {
+        for (int j = tid; j < ncubes; j += EMIT_THREADS) {
             int lo = 0, hi = 255;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
@@ -455,16 +501,19 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
             int x = 0;
             for (int q = 0; q <= kth; ++q, before &= before - 1) {     // triangles of the earlier cubes of the row
                 x = __ffs(before) - 1;
-                if (q < kth) tbase += MC_TRI_COUNT[cube_case(s00, s10, s01, s11, x + 1)];
+                if (q < kth) tbase += (int)(__ldg(&MC_TRI_PACKED[cube_case(s00, s10, s01, s11, x + 1)]) >> 60);
             }
             {
-                const int c = cube_case(s00, s10, s01, s11, x + 1);
-                for (int k = 0; k < 15 && s_tt[c * 16 + k] >= 0; k += 3, ++tbase) {
+                // the case's triangle list: 4-bit edge ids, three per triangle (one 64-bit load, L1-resident table)
+                unsigned long long tt = __ldg(&MC_TRI_PACKED[cube_case(s00, s10, s01, s11, x + 1)]);
+                const int n_tri = (int)(tt >> 60);
+                for (int k = 0; k < n_tri; ++k, ++tbase) {
 #pragma unroll
-                    for (int vtx = 0; vtx < 3; ++vtx) {
-                        const int edge = s_tt[c * 16 + k + vtx];
-                        const int ox = x + MC_EDGE_SHIFTS[edge][0], oy = y + MC_EDGE_SHIFTS[edge][1],
-                                  oz = z + MC_EDGE_SHIFTS[edge][2], ax = MC_EDGE_SHIFTS[edge][3];
+                    for (int vtx = 0; vtx < 3; ++vtx, tt >>= 4) {
+                        const int edge = (int)(tt & 15ull);
+                        const unsigned sh = (unsigned)(MC_EDGE_SHIFT_BITS >> (5 * edge)) & 31u;   // dx | dy<<1 | dz<<2 | axis<<3
+                        const int ox = x + (int)(sh & 1u), oy = y + (int)((sh >> 1) & 1u), oz = z + (int)((sh >> 2) & 1u);
+                        const int ax = (int)(sh >> 3);
                         const int nbk = nb_of(ox) + 3 * nb_of(oy) + 9 * nb_of(oz);
                         const int item = ax * 256 + (oz & 15) * 16 + (oy & 15);
                         const unsigned low = (1u << (ox & 15)) - 1u;
@@ -594,7 +643,9 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
     MQ3D_REQUIRE(n <= g->capacity, "internal: block count exceeds pool capacity");
     if (n > g->mc_alloc_blocks || g->mc_offsets == nullptr) {
         cudaFree(g->mc_nb); cudaFree(g->mc_emask); cudaFree(g->mc_eprefix); cudaFree(g->mc_counts); cudaFree(g->mc_offsets);
+        cudaFree(g->mc_totals);
         g->mc_nb = nullptr; g->mc_emask = nullptr; g->mc_eprefix = nullptr; g->mc_counts = nullptr; g->mc_offsets = nullptr;
+        g->mc_totals = nullptr;
         g->mc_alloc_blocks = 0;
         int64_t a = n + n / 4 + 16;
         MQ3D_CUDA(cudaMalloc(&g->mc_nb, sizeof(int32_t) * 27 * a));
@@ -602,6 +653,7 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
         MQ3D_CUDA(cudaMalloc(&g->mc_eprefix, sizeof(uint16_t) * R16_WORDS * a));    // 16-bit row tables
         MQ3D_CUDA(cudaMalloc(&g->mc_counts, sizeof(int32_t) * 2 * a));
         MQ3D_CUDA(cudaMalloc(&g->mc_offsets, sizeof(int64_t) * 2 * (a + 1)));
+        MQ3D_CUDA(cudaMalloc(&g->mc_totals, sizeof(long long) * 2 * (a / SCAN_CHUNK + 2)));
         g->mc_alloc_blocks = a;
     }
     g->mc_blocks = n;
@@ -612,10 +664,22 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
     return MQ3D_OK;
 }
 
+static int mc_scan(mq3d_grid *g, cudaStream_t st) {
+    const int64_t n = g->mc_blocks;
+    const unsigned chunks = (unsigned)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    k_scan_totals<<<chunks, SCAN_THREADS, 0, st>>>(g->mc_counts, n, g->mc_totals);
+    k_scan_counts<<<chunks, SCAN_THREADS, 0, st>>>(g->mc_counts, n, g->mc_totals, g->mc_offsets);
+    MQ3D_CUDA(cudaGetLastError());
+    return MQ3D_OK;
+}
+
 static int mc_finish_count(mq3d_grid *g, cudaStream_t st, int64_t *a, int64_t *b) {
     int64_t n = g->mc_blocks;
-    k_scan_counts<<<1, 1024, 0, st>>>(g->mc_counts, n, g->mc_offsets);
-    MQ3D_CUDA(cudaGetLastError());
+    if (n > 0) {
+        MQ3D_TRY(mc_scan(g, st));
+    } else {
+        MQ3D_CUDA(cudaMemsetAsync(g->mc_offsets, 0, sizeof(int64_t) * 2, st));
+    }
     MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host64, g->mc_offsets + 2 * n, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
     MQ3D_CUDA(cudaStreamSynchronize(st));
     *a = g->pinned_host64[0];
@@ -645,6 +709,46 @@ extern "C" int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int
     return MQ3D_OK;
 }
 
+extern "C" int mq3d_extract_mesh(mq3d_grid *g, float weight_threshold, float *vertices_dev, float *normals_dev,
+                                 int32_t *triangles_dev, int32_t *vertex_keys_dev, float *colors_dev, int64_t cap_vertices,
+                                 int64_t cap_triangles, int64_t *n_vertices, int64_t *n_triangles, void *stream) {
+    MQ3D_REQUIRE(g && n_vertices && n_triangles, "null argument");
+    MQ3D_REQUIRE(cap_vertices >= 0 && cap_triangles >= 0, "negative capacity");
+    MQ3D_REQUIRE(cap_vertices == 0 || vertices_dev, "null vertex buffer");
+    MQ3D_REQUIRE(colors_dev == nullptr || g->color != nullptr, "grid has no colour attribute");
+    MQ3D_TRY(mq3d_set_device(g->device));
+    cudaStream_t st = as_stream(stream);
+    g->mc_state = 0;
+    MQ3D_TRY(mc_prepare(g, st));
+    const int64_t n = g->mc_blocks;
+    if (n > 0) {
+        k_mc_classify<<<(unsigned)n, MC_CLASSIFY_THREADS, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, n, weight_threshold, g->part,
+                                                   g->mc_emask, g->mc_eprefix, g->mc_counts);
+        MQ3D_TRY(mc_scan(g, st));
+        // emission is enqueued at once: the kernels read the totals on the device and do nothing if the mesh does not
+        // fit -- no host round trip between classification and emission
+        k_mc_emit<<<(unsigned)n, EMIT_THREADS, 0, st>>>(g->tsdf, g->block_keys, g->mc_nb, g->mc_emask, g->mc_eprefix, g->mc_counts,
+                                                        g->mc_offsets, g->voxel_size, vertices_dev, normals_dev, triangles_dev,
+                                                        vertex_keys_dev, n, cap_vertices, cap_triangles);
+        if (colors_dev)
+            k_mc_colors<<<(unsigned)n, EMIT_THREADS, 0, st>>>(g->tsdf, g->color, g->mc_nb, g->mc_eprefix, g->mc_counts, g->mc_offsets,
+                                                              colors_dev, n, cap_vertices, cap_triangles);
+        MQ3D_CUDA(cudaGetLastError());
+        MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host64, g->mc_offsets + 2 * n, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
+        MQ3D_CUDA(cudaStreamSynchronize(st));
+        g->mc_V = g->pinned_host64[0];
+        g->mc_T = g->pinned_host64[1];
+    } else {
+        g->mc_V = g->mc_T = 0;
+    }
+    MQ3D_REQUIRE(g->mc_V < 2147483647LL && g->mc_T < 2147483647LL, "mesh too large for int32 indices");
+    *n_vertices = g->mc_V;
+    *n_triangles = g->mc_T;
+    g->mc_weight_thr = weight_threshold;
+    g->mc_state = 1;       // classified: mq3d_extract_mesh_fill / _colors may follow (needed when the mesh did not fit)
+    return MQ3D_OK;
+}
+
 extern "C" int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *normals_dev, int32_t *triangles_dev,
                                       int32_t *vertex_keys_dev, void *stream) {
     MQ3D_REQUIRE(g != nullptr, "null grid");
@@ -656,9 +760,9 @@ extern "C" int mq3d_extract_mesh_fill(mq3d_grid *g, float *vertices_dev, float *
     MQ3D_TRY(mq3d_set_device(g->device));
     cudaStream_t st = as_stream(stream);
     if (g->mc_blocks > 0 && (g->mc_V > 0 || g->mc_T > 0)) {
-        k_mc_emit<<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->block_keys, g->mc_nb, g->mc_emask, g->mc_eprefix,
-                                                          g->mc_counts, g->mc_offsets, g->voxel_size, vertices_dev,
-                                                          normals_dev, triangles_dev, vertex_keys_dev);
+        k_mc_emit<<<(unsigned)g->mc_blocks, EMIT_THREADS, 0, st>>>(g->tsdf, g->block_keys, g->mc_nb, g->mc_emask, g->mc_eprefix,
+                                                                   g->mc_counts, g->mc_offsets, g->voxel_size, vertices_dev,
+                                                                   normals_dev, triangles_dev, vertex_keys_dev, g->mc_blocks, -1, -1);
         MQ3D_CUDA(cudaGetLastError());
     }
     return MQ3D_OK;
@@ -715,8 +819,8 @@ extern "C" int mq3d_extract_mesh_colors(mq3d_grid *g, float *colors_dev, void *s
     MQ3D_TRY(mq3d_set_device(g->device));
     cudaStream_t st = as_stream(stream);
     if (g->mc_blocks > 0 && g->mc_V > 0) {
-        k_mc_colors<<<(unsigned)g->mc_blocks, 256, 0, st>>>(g->tsdf, g->color, g->mc_nb, g->mc_eprefix, g->mc_counts,
-                                                            g->mc_offsets, colors_dev);
+        k_mc_colors<<<(unsigned)g->mc_blocks, EMIT_THREADS, 0, st>>>(g->tsdf, g->color, g->mc_nb, g->mc_eprefix, g->mc_counts,
+                                                                     g->mc_offsets, colors_dev, g->mc_blocks, -1, -1);
         MQ3D_CUDA(cudaGetLastError());
     }
     return MQ3D_OK;

@@ -403,22 +403,47 @@ class VoxelBlockGrid:
     def extract_triangle_mesh_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False,
                                      with_colors: bool = False):
         """(vertices f32 [V,3], normals f32 [V,3], triangles i32 [T,3][, vertex_keys i32 [V,4]][, colors f32
-        [V,3] in 0..1]) on device; colours need the colour attribute."""
+        [V,3] in 0..1]) on device; colours need the colour attribute.
+
+        The first extraction of a grid uses the count -> allocate -> fill pair; later ones allocate from the sizes
+        seen before (with head room) and make ONE library call (mq3d_extract_mesh: classification, scan and emission
+        enqueued back to back, one synchronisation), falling back to an exact-size fill if the mesh outgrew the
+        guess.  The returned tensors are then leading-row views of slightly larger buffers."""
         V, T = C.c_int64(), C.c_int64()
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().mq3d_extract_mesh_count(self._h, C.c_float(weight_threshold), C.byref(V),
-                                                          C.byref(T), _stream()))
-            verts = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
-            normals = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
-            tris = torch.empty((T.value, 3), dtype=torch.int32, device=self.device)
-            vkeys = torch.empty((V.value, 4), dtype=torch.int32, device=self.device) if with_keys else None
-            _lib.check(_lib.lib().mq3d_extract_mesh_fill(self._h, _lib.dptr(verts), _lib.dptr(normals),
-                                                         _lib.dptr(tris), _lib.dptr(vkeys), _stream()))
-            out = (verts, normals, tris) + ((vkeys,) if with_keys else ())
-            if with_colors:
-                cols = torch.empty((V.value, 3), dtype=torch.float32, device=self.device)
-                _lib.check(_lib.lib().mq3d_extract_mesh_colors(self._h, _lib.dptr(cols), _stream()))
-                out += (cols,)
+        dev = self.device
+        with torch.cuda.device(dev):
+            def alloc(nv, nt):
+                return (torch.empty((nv, 3), dtype=torch.float32, device=dev),
+                        torch.empty((nv, 3), dtype=torch.float32, device=dev),
+                        torch.empty((nt, 3), dtype=torch.int32, device=dev),
+                        torch.empty((nv, 4), dtype=torch.int32, device=dev) if with_keys else None,
+                        torch.empty((nv, 3), dtype=torch.float32, device=dev) if with_colors else None)
+
+            def fill(bufs):
+                _lib.check(_lib.lib().mq3d_extract_mesh_fill(self._h, _lib.dptr(bufs[0]), _lib.dptr(bufs[1]),
+                                                             _lib.dptr(bufs[2]), _lib.dptr(bufs[3]), _stream()))
+                if with_colors:
+                    _lib.check(_lib.lib().mq3d_extract_mesh_colors(self._h, _lib.dptr(bufs[4]), _stream()))
+
+            cap = getattr(self, "_mesh_cap", None)
+            if cap is None:
+                _lib.check(_lib.lib().mq3d_extract_mesh_count(self._h, C.c_float(weight_threshold), C.byref(V),
+                                                              C.byref(T), _stream()))
+                bufs = alloc(V.value, T.value)
+                fill(bufs)
+            else:
+                bufs = alloc(*cap)
+                _lib.check(_lib.lib().mq3d_extract_mesh(self._h, C.c_float(weight_threshold), _lib.dptr(bufs[0]),
+                                                        _lib.dptr(bufs[1]), _lib.dptr(bufs[2]), _lib.dptr(bufs[3]),
+                                                        _lib.dptr(bufs[4]), cap[0], cap[1], C.byref(V), C.byref(T),
+                                                        _stream()))
+                if V.value > cap[0] or T.value > cap[1]:
+                    bufs = alloc(V.value, T.value)
+                    fill(bufs)
+            self._mesh_cap = (V.value + V.value // 8 + 1024, T.value + T.value // 8 + 1024)
+            verts, normals, tris, vkeys, cols = (None if x is None else x[: (T.value if i == 2 else V.value)]
+                                                 for i, x in enumerate(bufs))
+            out = (verts, normals, tris) + ((vkeys,) if with_keys else ()) + ((cols,) if with_colors else ())
         return out
 
     def extract_point_cloud_arrays(self, weight_threshold: float = 3.0, with_keys: bool = False,

@@ -57,3 +57,32 @@ def test_mesh_fill_requires_count(cuda_device, oracle):
     assert rc == _lib.MQ3D_ERR_STATE
     v, n, t = vbg.extract_triangle_mesh_arrays(1.5)    # empty grid -> empty mesh
     assert v.shape == (0, 3) and t.shape == (0, 3)
+
+
+def test_single_call_extraction_equals_count_fill(cuda_device, oracle):
+    """mq3d_extract_mesh (classification, scan and emission enqueued without a host round trip, sizes bounded by the
+    previous extraction) returns the very arrays of the count -> fill pair -- also when the mesh outgrew the bound
+    (the kernels then write nothing and the exact-size fill follows), and for an empty result."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    og, vbg = _grids(oracle, cuda_device)
+    first = [x.cpu().numpy() for x in vbg.extract_triangle_mesh_arrays(1.5, with_keys=True)]      # count -> fill
+    assert vbg._mesh_cap[0] >= len(first[0])
+    second = [x.cpu().numpy() for x in vbg.extract_triangle_mesh_arrays(1.5, with_keys=True)]     # single call
+    for a, b in zip(first, second):
+        assert a.dtype == b.dtype and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                                     b.view(np.uint32) if b.dtype == np.float32 else b)
+    # a bound that is too small: nothing is written by the capped kernels, the fallback fills exact buffers
+    vbg._mesh_cap = (len(first[0]) // 2, len(first[2]) // 2)
+    third = [x.cpu().numpy() for x in vbg.extract_triangle_mesh_arrays(1.5, with_keys=True)]
+    vbg._mesh_cap = (len(first[0]) + 5, len(first[2]) // 2)              # only the triangles do not fit
+    fourth = [x.cpu().numpy() for x in vbg.extract_triangle_mesh_arrays(1.5, with_keys=True)]
+    for got in (third, fourth):
+        for a, b in zip(first, got):
+            assert np.array_equal(a, b)
+    # threshold above every weight: empty mesh through the single call
+    v, n, t = vbg.extract_triangle_mesh_arrays(1e9)
+    assert v.shape == (0, 3) and t.shape == (0, 3)
+    empty = VoxelBlockGrid(voxel_size=0.02, block_count=100, device=cuda_device)
+    empty._mesh_cap = (10, 10)
+    v, n, t = empty.extract_triangle_mesh_arrays(1.5)
+    assert v.shape == (0, 3) and t.shape == (0, 3)
