@@ -213,6 +213,7 @@ struct mq3d_grid {
     float *tsdf, *weight, *color;
     int *n_blocks_dev;    // device counter (may exceed capacity transiently; host grows the pool)
     int64_t n_blocks_host;  // last synchronised value
+    int count_dirty;        // blocks may have been added on the device since n_blocks_host was read
     // per-frame touch scratch ("frustum hashmap")
     HashView frustum;
     int64_t frustum_size;
@@ -252,8 +253,9 @@ struct mq3d_grid {
     int n_events;
     // marching cubes scratch (valid between *_count and *_fill)
     int32_t *mc_nb;       // [n][27]
-    uint32_t *mc_emask;   // [n][384]
-    uint16_t *mc_eprefix; // [n][384]
+    uint32_t *mc_rows;    // [n][256] (validity << 16) | sign of every x-row
+    uint32_t *mc_emask;   // [n][324] 18-bit sign rows of the (-1..16)^2 neighbourhood
+    uint16_t *mc_eprefix; // [n][2304] 16-bit row tables (edge marks, prefixes, surface cubes)
     int32_t *mc_counts;   // [n][2] vertices, triangles (or points)
     int64_t *mc_offsets;  // [n+1][2]
     long long *mc_totals; // [chunks][2] partial sums of the count scan
@@ -264,7 +266,8 @@ struct mq3d_grid {
     int64_t mc_V, mc_T;
 };
 
-int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st);                 // refresh n_blocks_host
+int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st);                 // refresh n_blocks_host (synchronises)
+int mq3d_grid_fresh_count(mq3d_grid *g, cudaStream_t st);                // same, but only if blocks may have been added since
 int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool *rehashed);
 int mq3d_set_device(int device);
 // Activate + Find for an explicit key list; block indices land in g->idx_scratch.

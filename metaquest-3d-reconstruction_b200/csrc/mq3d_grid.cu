@@ -188,12 +188,14 @@ static void free_mc(mq3d_grid *g) {
     cudaFree(g->mc_counts);
     cudaFree(g->mc_offsets);
     cudaFree(g->mc_totals);
+    cudaFree(g->mc_rows);
     g->mc_nb = nullptr;
     g->mc_emask = nullptr;
     g->mc_eprefix = nullptr;
     g->mc_counts = nullptr;
     g->mc_offsets = nullptr;
     g->mc_totals = nullptr;
+    g->mc_rows = nullptr;
     g->mc_alloc_blocks = 0;
     g->mc_state = 0;
 }
@@ -402,7 +404,12 @@ int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st) {
     MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host, g->n_blocks_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     MQ3D_CUDA(cudaStreamSynchronize(st));
     g->n_blocks_host = g->pinned_host[0];
+    g->count_dirty = 0;
     return MQ3D_OK;
+}
+
+int mq3d_grid_fresh_count(mq3d_grid *g, cudaStream_t st) {
+    return g->count_dirty ? mq3d_grid_sync_count(g, st) : MQ3D_OK;
 }
 
 extern "C" int mq3d_grid_num_blocks(mq3d_grid *g, int64_t *n, void *stream) {
@@ -476,7 +483,7 @@ extern "C" int mq3d_grid_reset(mq3d_grid *g, void *stream) {
     MQ3D_REQUIRE(g != nullptr, "null grid");
     MQ3D_TRY(mq3d_set_device(g->device));
     cudaStream_t st = as_stream(stream);
-    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    MQ3D_TRY(mq3d_grid_fresh_count(g, st));
     int64_t live = g->n_blocks_host < g->capacity ? g->n_blocks_host : g->capacity;
     k_fill_u64<<<1184, 256, 0, st>>>(g->hash.keys, MQ3D_EMPTY_KEY, g->table_size);
     MQ3D_CUDA(cudaMemsetAsync(g->hash.vals, 0xFF, sizeof(int32_t) * g->table_size, st));
@@ -485,8 +492,8 @@ extern "C" int mq3d_grid_reset(mq3d_grid *g, void *stream) {
     if (g->color) MQ3D_CUDA(cudaMemsetAsync(g->color, 0, sizeof(float) * 3 * MQ3D_RES3 * live, st));
     MQ3D_CUDA(cudaMemsetAsync(g->n_blocks_dev, 0, sizeof(int), st));
     MQ3D_CUDA(cudaMemsetAsync(g->bitmap, 0, sizeof(uint32_t) * g->table_size * g->bitmap_words, st));
-    MQ3D_CUDA(cudaStreamSynchronize(st));
     g->n_blocks_host = 0;
+    g->count_dirty = 0;
     g->mc_state = 0;
     return MQ3D_OK;
 }
@@ -582,6 +589,7 @@ int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool in
                                           g->part, integrating, g->counter_dev);
     k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->part, integrating, g->idx_scratch);
     MQ3D_CUDA(cudaGetLastError());
+    g->count_dirty = 1;
     g->mc_state = 0;
     return MQ3D_OK;
 }

@@ -5,9 +5,11 @@
 // (reference: processing/reconstruction/reconstruct_scene.py:90,105-108,186-189).
 //
 // GPU formulation (no global 16 B/voxel "mesh_structure" volume, no global atomics):
-//   classify (one CTA per block): the validity (exists && w > thr) and sign (tsdf < 0) of the
-//     (-1..16)^3 neighbourhood are reduced to 18-bit ROWS along x while they are loaded (float4 for
-//     the 16-voxel interior of a row).  Everything else is row-wise bit arithmetic: cube validity
+//   rows (streaming, one thread per 16-voxel x-row): tsdf and weight of every resident block are read exactly
+//     once, fully coalesced, and reduced to a 16-bit validity row (w > thr) and a 16-bit sign row (tsdf < 0) --
+//     1 KiB per block instead of 32 KiB; this is the only pass over the voxel data;
+//   classify (one CTA per block): the 18-bit rows of the (-1..16)^3 neighbourhood are assembled from the block's
+//     and its neighbours' 16-bit rows (L2-resident).  Everything else is row-wise bit arithmetic: cube validity
 //     = AND of four rows and their shift, "surface" cubes = valid cubes whose 8 signs differ, edge
 //     marks = sign difference AND (OR of the four cubes sharing the edge).  Per block it stores
 //     16-bit edge-mark rows for the three axes, their exclusive prefix counts, the surface-cube rows,
@@ -20,6 +22,8 @@
 //     cube row walks its surface cubes and writes triangles with ids resolved through the bit rows.
 // Output order is deterministic.  A cube counts on this rank only if its block is owned (multi-GPU
 // partition); single-GPU grids own every block.
+#include <stdlib.h>
+
 #include "mc_tables.h"
 #include "mq3d_common.cuh"
 
@@ -32,7 +36,8 @@
 #define R16_SURF 1536    // [256]    surface cubes of the own rows, bit x
 #define R16_TPREF 1792   // [256]    exclusive prefix of per-row triangle counts
 #define R16_SPREF 2048   // [256]    exclusive prefix of per-row surface-cube counts
-#define R16_WORDS 2304
+#define R16_TPLANE 2304  // [3][256] bit planes of the per-cube triangle counts: bit x of plane k = bit k of the count of cube x
+#define R16_WORDS 3072
 
 __device__ __forceinline__ int nb_of(int r) { return r < 0 ? 0 : (r > 15 ? 2 : 1); }  // -> d+1
 
@@ -85,86 +90,101 @@ __device__ __forceinline__ int cube_case(unsigned s00, unsigned s10, unsigned s0
 // ------------------------------------------------------------------------------------------------
 // classify
 // ------------------------------------------------------------------------------------------------
-#define MC_CLASSIFY_THREADS 352   // 11 warps: 324 neighbourhood rows in phase A, 289 cube rows in B, 256 own rows in C
-// One CTA per block.  The kernel is latency-bound (one DRAM round trip + a chain of block barriers per
-// 37 KB block), so the chain is kept short: neighbour indices are read by the threads that need them (no
-// staging barrier), the five per-row counts are scanned in registers with warp shuffles (no serial
-// warp-0 scan), three barriers.  (A persistent cp.async-staged variant was measured slower: 0.51 vs 0.30 ms
-// on 17 k blocks.)
-__global__ void __launch_bounds__(MC_CLASSIFY_THREADS, 4)
-k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, const int32_t *__restrict__ block_keys,
-              const int32_t *__restrict__ nb, int64_t n_blocks, float weight_thr, Partition part,
+// One thread per x-row of a block: 16 tsdf + 16 weight floats (four float4 each, a warp reads 2 KiB contiguous of
+// both arrays) -> (validity << 16) | sign, bit x.  No neighbour table, no barriers: the pass over the voxel data
+// runs at memory speed.  Open3D rejects `w <= thr`.
+__global__ void __launch_bounds__(256)
+k_mc_rows(const float *__restrict__ tsdf, const float *__restrict__ weight, int64_t n_blocks, float weight_thr,
+          uint32_t *__restrict__ rows_vs) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;    // global row index: block * 256 + z * 16 + y
+    if (r >= n_blocks * 256) return;
+    const float4 *t4 = reinterpret_cast<const float4 *>(tsdf) + r * 4;
+    const float4 *w4 = reinterpret_cast<const float4 *>(weight) + r * 4;
+    float4 tq[4], wq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        tq[q] = __ldcs(t4 + q);
+        wq[q] = __ldcs(w4 + q);
+    }
+    unsigned vrow = 0, srow = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        vrow |= ((wq[q].x > weight_thr ? 1u : 0u) | (wq[q].y > weight_thr ? 2u : 0u) | (wq[q].z > weight_thr ? 4u : 0u) |
+                 (wq[q].w > weight_thr ? 8u : 0u)) << (4 * q);
+        srow |= ((tq[q].x < 0.0f ? 1u : 0u) | (tq[q].y < 0.0f ? 2u : 0u) | (tq[q].z < 0.0f ? 4u : 0u) |
+                 (tq[q].w < 0.0f ? 8u : 0u)) << (4 * q);
+    }
+    rows_vs[r] = (vrow << 16) | srow;
+}
+
+#define MC_CLASSIFY_THREADS 256
+// One CTA per block, working on the 16-bit rows of k_mc_rows only (a few KiB per block, L2-resident): neighbour
+// indices are read by the threads that need them (no staging barrier), cube validity is recomputed by the rows
+// that need it (no second staging barrier), the five per-row counts are scanned in registers with warp shuffles
+// (no serial warp-0 scan): two barriers per block, 6 CTAs per SM to hide what latency remains.
+__global__ void __launch_bounds__(MC_CLASSIFY_THREADS, 6)
+k_mc_classify(const uint32_t *__restrict__ rows_vs, const int32_t *__restrict__ block_keys,
+              const int32_t *__restrict__ nb, int64_t n_blocks, Partition part,
               uint32_t *__restrict__ srow_out, uint16_t *__restrict__ rows16, int32_t *__restrict__ counts) {
     __shared__ unsigned s_valid[SROW_WORDS], s_sign[SROW_WORDS];
-    __shared__ unsigned s_cok[17 * 17];
-    __shared__ int s_wtot[8][5];
+    __shared__ unsigned s_own[4];            // ownership masks of the cube rows with (cube y == -1, cube z == -1) = bits of the index
+    __shared__ int s_wtot[8][3];
     __shared__ unsigned char s_tc[256];      // triangles per cube case (constant-bank reads with a per-lane index serialise)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
-    if (tid < 256) s_tc[tid] = (unsigned char)(__ldg(&MC_TRI_PACKED[tid]) >> 60);   // read in phase C, two barriers later
+    s_tc[tid] = (unsigned char)(__ldg(&MC_TRI_PACKED[tid]) >> 60);
     {
-        // ---- phase A: one thread per (y,z) row of the (-1..16)^2 neighbourhood: the 16 interior voxels as
-        // four float4 of tsdf and of weight, the x=-1 / x=16 columns as scalars from the -x / +x neighbour
-        // blocks; branch-free (missing blocks read this block's own row and are masked), 12 loads in flight
-        // per thread, bits assembled in registers (no shared-memory atomics).
-        if (tid < SROW_WORDS) {
-            const int r = tid;
+        // ---- phase A: one thread per (y,z) row of the (-1..16)^2 neighbourhood: the row's 16 interior bits from the
+        // block that holds it, the x = -1 / x = 16 bits from that block's -x / +x neighbours (bit i <-> x = i - 1);
+        // missing blocks contribute zeros
+        for (int r = tid; r < SROW_WORDS; r += MC_CLASSIFY_THREADS) {
             const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
             const int k0 = 3 * nb_of(ry) + 9 * nb_of(rz);
             const int bm = __ldg(nb + b * 27 + k0), b0 = __ldg(nb + b * 27 + k0 + 1), bp = __ldg(nb + b * 27 + k0 + 2);
-            const int ro = ((rz & 15) * 16 + (ry & 15)) * 16;
-            const float *t0 = tsdf + (int64_t)(b0 < 0 ? (int)b : b0) * MQ3D_RES3 + ro;
-            const float *w0 = weight + (int64_t)(b0 < 0 ? (int)b : b0) * MQ3D_RES3 + ro;
-            const int64_t om = (int64_t)(bm < 0 ? (int)b : bm) * MQ3D_RES3 + ro + 15;
-            const int64_t op = (int64_t)(bp < 0 ? (int)b : bp) * MQ3D_RES3 + ro;
-            float4 tq[4], wq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                tq[q] = __ldg(reinterpret_cast<const float4 *>(t0) + q);
-                wq[q] = __ldg(reinterpret_cast<const float4 *>(w0) + q);
-            }
-            const float tm = __ldg(tsdf + om), wm = __ldg(weight + om), tp = __ldg(tsdf + op), wp = __ldg(weight + op);
-            unsigned vrow = 0, srow = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                // Open3D rejects `w <= thr`
-                vrow |= ((wq[q].x > weight_thr ? 1u : 0u) | (wq[q].y > weight_thr ? 2u : 0u) | (wq[q].z > weight_thr ? 4u : 0u) |
-                         (wq[q].w > weight_thr ? 8u : 0u)) << (1 + 4 * q);
-                srow |= ((tq[q].x < 0.0f ? 1u : 0u) | (tq[q].y < 0.0f ? 2u : 0u) | (tq[q].z < 0.0f ? 4u : 0u) |
-                         (tq[q].w < 0.0f ? 8u : 0u)) << (1 + 4 * q);
-            }
-            if (b0 < 0) vrow = srow = 0;
-            if (bm >= 0) { vrow |= (wm > weight_thr ? 1u : 0u); srow |= (tm < 0.0f ? 1u : 0u); }
-            if (bp >= 0) { vrow |= (wp > weight_thr ? 1u : 0u) << 17; srow |= (tp < 0.0f ? 1u : 0u) << 17; }
+            const int ri = (rz & 15) * 16 + (ry & 15);
+            const unsigned w0 = b0 >= 0 ? __ldg(rows_vs + (int64_t)b0 * 256 + ri) : 0u;
+            const unsigned wm = bm >= 0 ? __ldg(rows_vs + (int64_t)bm * 256 + ri) : 0u;
+            const unsigned wp = bp >= 0 ? __ldg(rows_vs + (int64_t)bp * 256 + ri) : 0u;
+            const unsigned vrow = ((w0 >> 16) << 1) | (wm >> 31) | (((wp >> 16) & 1u) << 17);
+            const unsigned srow = ((w0 & 0xFFFFu) << 1) | ((wm >> 15) & 1u) | ((wp & 1u) << 17);
             s_valid[r] = vrow;
             s_sign[r] = srow;
             srow_out[b * SROW_WORDS + r] = srow;
         }
-        __syncthreads();
-    // ---- phase B: valid (and owned) cubes of the cube rows (cy,cz) in -1..15, bit i <-> cube x = i-1 ----
-    if (tid < 17 * 17) {
-        const int c = tid;
-        const int cy = c % 17, cz = c / 17;      // region row index of the cube's low corner (cube y = cy-1)
-        const unsigned m = s_valid[cz * ROW_R + cy] & s_valid[cz * ROW_R + cy + 1] & s_valid[(cz + 1) * ROW_R + cy] &
-                           s_valid[(cz + 1) * ROW_R + cy + 1];
-        unsigned ok = m & (m >> 1) & 0x1FFFFu;
-        if (part.world > 1) {                    // cubes count only in owned blocks; cube y/z = -1 -> block -1
-            const int kx = block_keys[3 * b], ky = block_keys[3 * b + 1] + (cy == 0 ? -1 : 0),
-                      kz = block_keys[3 * b + 2] + (cz == 0 ? -1 : 0);
-            ok &= (mq3d_block_owned(kx - 1, ky, kz, part) ? 1u : 0u) | (mq3d_block_owned(kx, ky, kz, part) ? 0x1FFFEu : 0u);
+        if (tid < 4) {
+            // cubes count only in owned blocks (multi-GPU partition); cube x = -1 lies in block x - 1, cube y / z = -1 in
+            // block y - 1 / z - 1.  Bit 0 <-> cube x = -1, bits 1..16 <-> cubes of this block's x range.
+            unsigned own = 0x1FFFFu;
+            if (part.world > 1) {
+                const int kx = block_keys[3 * b], ky = block_keys[3 * b + 1] - (tid & 1), kz = block_keys[3 * b + 2] - (tid >> 1);
+                own = (mq3d_block_owned(kx - 1, ky, kz, part) ? 1u : 0u) | (mq3d_block_owned(kx, ky, kz, part) ? 0x1FFFEu : 0u);
+            }
+            s_own[tid] = own;
         }
-        s_cok[c] = ok;
-    }
-    __syncthreads();
+        __syncthreads();
     // ---- phase C: one thread per own row (y,z): edge marks, surface cubes, triangle count ----
     int cnt[5] = {0, 0, 0, 0, 0};   // popc(x marks), popc(y marks), popc(z marks), triangles, surface cubes
-    if (tid < 256) {
+    {
         const int y = tid & 15, z = tid >> 4;
+        // valid (and owned) cubes of the cube rows (y,z) (y-1,z) (y,z-1) (y-1,z-1), bit i <-> cube x = i-1: AND of the
+        // four neighbourhood rows around the cube row and of their shift by one (region row index = coordinate + 1)
+        unsigned v[3][3];
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) v[dz][dy] = s_valid[(z + dz) * ROW_R + y + dy];
+        unsigned cok[2][2];
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const unsigned m = v[dz][dy] & v[dz][dy + 1] & v[dz + 1][dy] & v[dz + 1][dy + 1];
+                // cube row (y - 1 + dy, z - 1 + dz)
+                cok[dz][dy] = m & (m >> 1) & s_own[((y + dy == 0) ? 1 : 0) | ((z + dz == 0) ? 2 : 0)];
+            }
+        const unsigned c00 = cok[1][1], cm0 = cok[1][0], c0m = cok[0][1], cmm = cok[0][0];
         const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
         const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
-        // cube rows (index = cube coord + 1): (y,z) (y-1,z) (y,z-1) (y-1,z-1)
-        const unsigned c00 = s_cok[(z + 1) * 17 + y + 1], cm0 = s_cok[(z + 1) * 17 + y];
-        const unsigned c0m = s_cok[z * 17 + y + 1], cmm = s_cok[z * 17 + y];
         const unsigned ex = (s00 ^ (s00 >> 1)) & (c00 | cm0 | c0m | cmm);
         const unsigned cy_ = c00 | c0m, cz_ = c00 | cm0;
         const unsigned ey = (s00 ^ s10) & (cy_ | (cy_ << 1));
@@ -174,54 +194,69 @@ k_mc_classify(const float *__restrict__ tsdf, const float *__restrict__ weight, 
         const unsigned same4 = ~((s00 ^ s10) | (s00 ^ s01) | (s00 ^ s11));
         const unsigned flat = same4 & (same4 >> 1) & ~(s00 ^ (s00 >> 1));
         const unsigned surf = (c00 & ~flat) >> 1 & 0xFFFFu;
-        int ntri = 0;
-        for (unsigned m = surf; m; m &= m - 1) ntri += s_tc[cube_case(s00, s10, s01, s11, __ffs(m))];
+        // triangles per surface cube, kept as three bit planes so that any cube's offset inside its row is a popcount
+        unsigned p0 = 0, p1 = 0, p2 = 0;
+        for (unsigned m = surf; m; m &= m - 1) {
+            const int i = __ffs(m);                           // cube x = i - 1
+            const unsigned t = s_tc[cube_case(s00, s10, s01, s11, i)];
+            p0 |= (t & 1u) << (i - 1);
+            p1 |= ((t >> 1) & 1u) << (i - 1);
+            p2 |= (t >> 2) << (i - 1);
+        }
+        const int ntri = __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
         uint16_t *r16 = rows16 + b * R16_WORDS;
         r16[R16_EMASK + tid] = (uint16_t)mx;
         r16[R16_EMASK + 256 + tid] = (uint16_t)my;
         r16[R16_EMASK + 512 + tid] = (uint16_t)mz;
         r16[R16_SURF + tid] = (uint16_t)surf;
+        r16[R16_TPLANE + tid] = (uint16_t)p0;
+        r16[R16_TPLANE + 256 + tid] = (uint16_t)p1;
+        r16[R16_TPLANE + 512 + tid] = (uint16_t)p2;
         cnt[0] = __popc(mx); cnt[1] = __popc(my); cnt[2] = __popc(mz); cnt[3] = ntri; cnt[4] = __popc(surf);
     }
-    // block-wide exclusive scans of the five counts over the 256 rows: warp shuffles + 8 warp totals
-    int incl[5];
+    // block-wide exclusive scans of the five counts over the 256 rows, packed into three words (every prefix stays
+    // below 2^16: at most 4096 edges per axis, 4096 cubes and 5 * 4096 triangles per block): warp shuffles, then the
+    // 8 warp totals are scanned by 8 lanes of every warp
+    unsigned pk[3] = {(unsigned)cnt[0] | ((unsigned)cnt[1] << 16), (unsigned)cnt[2] | ((unsigned)cnt[3] << 16), (unsigned)cnt[4]};
+    unsigned incl[3];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        int v = cnt[k];
+    for (int k = 0; k < 3; ++k) {
+        unsigned v = pk[k];
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, o);
             if (lane >= o) v += t;
         }
         incl[k] = v;
-        if (lane == 31 && warp < 8) s_wtot[warp][k] = v;
+        if (lane == 31) s_wtot[warp][k] = (int)v;
     }
     __syncthreads();
-    if (tid < 256) {
-        int base[5], tot[5];
+    {
+        unsigned base[3], tot[3];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            base[k] = 0;
-            tot[k] = 0;
-            for (int w = 0; w < 8; ++w) {
-                const int t = s_wtot[w][k];
-                if (w < warp) base[k] += t;
-                tot[k] += t;
+        for (int k = 0; k < 3; ++k) {
+            const unsigned own = lane < 8 ? (unsigned)s_wtot[lane][k] : 0u;
+            unsigned v = own;
+            for (int o = 1; o < 8; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= o) v += t;
             }
+            base[k] = __shfl_sync(0xFFFFFFFFu, v - own, warp);     // totals of the warps before this one
+            tot[k] = __shfl_sync(0xFFFFFFFFu, v, 7);
         }
+        const unsigned ex0 = base[0] + incl[0] - pk[0], ex1 = base[1] + incl[1] - pk[1], ex2 = base[2] + incl[2] - pk[2];
+        const unsigned tx = tot[0] & 0xFFFFu, ty = tot[0] >> 16, tz = tot[1] & 0xFFFFu;
         uint16_t *r16 = rows16 + b * R16_WORDS;
         // vertex numbering is axis-major: x edges, then y edges, then z edges
-        r16[R16_EPREF + tid] = (uint16_t)(base[0] + incl[0] - cnt[0]);
-        r16[R16_EPREF + 256 + tid] = (uint16_t)(tot[0] + base[1] + incl[1] - cnt[1]);
-        r16[R16_EPREF + 512 + tid] = (uint16_t)(tot[0] + tot[1] + base[2] + incl[2] - cnt[2]);
-        r16[R16_TPREF + tid] = (uint16_t)(base[3] + incl[3] - cnt[3]);
-        r16[R16_SPREF + tid] = (uint16_t)(base[4] + incl[4] - cnt[4]);
+        r16[R16_EPREF + tid] = (uint16_t)(ex0 & 0xFFFFu);
+        r16[R16_EPREF + 256 + tid] = (uint16_t)(tx + (ex0 >> 16));
+        r16[R16_EPREF + 512 + tid] = (uint16_t)(tx + ty + (ex1 & 0xFFFFu));
+        r16[R16_TPREF + tid] = (uint16_t)(ex1 >> 16);
+        r16[R16_SPREF + tid] = (uint16_t)ex2;
         if (tid == 0) {
-            counts[2 * b] = tot[0] + tot[1] + tot[2];
-            counts[2 * b + 1] = tot[3];
+            counts[2 * b] = (int)(tx + ty + tz);
+            counts[2 * b + 1] = (int)(tot[1] >> 16);
         }
     }
-        // (the barrier at the top of the next iteration orders this block's shared-memory reads before
-        //  the next block's writes)
     }
 }
 
@@ -359,15 +394,36 @@ __device__ __forceinline__ int64_t nb_lin(const int *s_nb, int x, int y, int z) 
 }
 
 // DeviceGetNormal on global memory: central differences where both neighbours exist; other components
-// keep their previous value (Open3D's caller-visible stale behaviour)
-__device__ __forceinline__ void get_normal_g(const float *__restrict__ tsdf, const int *s_nb, int x, int y, int z, float *n) {
-    int64_t p, m;
-    p = nb_lin(s_nb, x + 1, y, z); m = nb_lin(s_nb, x - 1, y, z);
-    if (p >= 0 && m >= 0) n[0] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
-    p = nb_lin(s_nb, x, y + 1, z); m = nb_lin(s_nb, x, y - 1, z);
-    if (p >= 0 && m >= 0) n[1] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
-    p = nb_lin(s_nb, x, y, z + 1); m = nb_lin(s_nb, x, y, z - 1);
-    if (p >= 0 && m >= 0) n[2] = __fsub_rn(__ldg(tsdf + p), __ldg(tsdf + m));
+// keep their previous value (Open3D's caller-visible stale behaviour).  The six loads are issued together
+// (a missing neighbour reads the voxel's own block start and is masked); returns the mask of the components
+// that were computed.
+__device__ __forceinline__ unsigned get_normal_g(const float *__restrict__ tsdf, const int *s_nb, int x, int y, int z, float *n) {
+    // neighbours inside the voxel's own block sit at +-1, +-16, +-256 from it; only voxels on a block face go
+    // through the neighbour table
+    const int64_t c = nb_lin(s_nb, x, y, z);
+    const int co[3] = {x & 15, y & 15, z & 15};
+    const int stride[3] = {1, 16, 256};
+    int64_t ip[3], im[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ip[a] = (co[a] < 15 && c >= 0) ? c + stride[a] : nb_lin(s_nb, x + (a == 0), y + (a == 1), z + (a == 2));
+        im[a] = (co[a] > 0 && c >= 0) ? c - stride[a] : nb_lin(s_nb, x - (a == 0), y - (a == 1), z - (a == 2));
+    }
+    float vp[3], vm[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        vp[a] = __ldg(tsdf + (ip[a] < 0 ? 0 : ip[a]));
+        vm[a] = __ldg(tsdf + (im[a] < 0 ? 0 : im[a]));
+    }
+    unsigned have = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (ip[a] >= 0 && im[a] >= 0) {
+            n[a] = __fsub_rn(vp[a], vm[a]);
+            have |= 1u << a;
+        }
+    }
+    return have;
 }
 
 // Open3D's colour branch of ExtractTriangleMesh / ExtractPointCloud: ((1-ratio)*c_o + ratio*c_e) / 255
@@ -443,7 +499,7 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
     if (tid < 27) s_nb[tid] = nb[b * 27 + tid];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(rows16 + b * R16_WORDS);
-        for (int i = tid; i < R16_WORDS / 8; i += EMIT_THREADS) reinterpret_cast<uint4 *>(s_r16)[i] = __ldg(src + i);   // 4.5 KB
+        for (int i = tid; i < R16_WORDS / 8; i += EMIT_THREADS) reinterpret_cast<uint4 *>(s_r16)[i] = __ldg(src + i);   // 6 KB
     }
     const bool do_tris = nt > 0 && tris != nullptr;
     if (do_tris)
@@ -469,14 +525,18 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
                 const float to = __ldg(tsdf + b * MQ3D_RES3 + row * 16 + x);
                 const float te = __ldg(tsdf + nb_lin(s_nb, ex, ey, ez));
                 const float ratio = __fdiv_rn(__fsub_rn(0.0f, to), __fsub_rn(te, to));
-                // Open3D keeps `ne` across the three edges of a voxel: components that cannot be
-                // recomputed at a later edge retain the value of the previous marked edge
+                // Open3D keeps `ne` across the three edges of a voxel: components that cannot be recomputed at a
+                // later edge retain the value of the previous marked edge.  That only shows when the end voxel
+                // lacks a neighbour (border of the allocated region): the common case needs this edge's gradient only.
                 float no[3] = {0.0f, 0.0f, 0.0f}, ne[3] = {0.0f, 0.0f, 0.0f};
                 get_normal_g(tsdf, s_nb, x, y, z, no);
-                for (int p = 0; p < e; ++p)
-                    if ((s_r16[R16_EMASK + p * 256 + row] >> x) & 1u)
-                        get_normal_g(tsdf, s_nb, x + (p == 0), y + (p == 1), z, ne);
-                get_normal_g(tsdf, s_nb, ex, ey, ez, ne);
+                if (get_normal_g(tsdf, s_nb, ex, ey, ez, ne) != 7u) {
+                    ne[0] = ne[1] = ne[2] = 0.0f;
+                    for (int p = 0; p < e; ++p)
+                        if ((s_r16[R16_EMASK + p * 256 + row] >> x) & 1u)
+                            get_normal_g(tsdf, s_nb, x + (p == 0), y + (p == 1), z, ne);
+                    get_normal_g(tsdf, s_nb, ex, ey, ez, ne);
+                }
                 write_vertex(verts, normals, vkeys, id, vs, kx * 16 + x, ky * 16 + y, kz * 16 + z, e, ratio, no, ne);
             }
         }
@@ -496,13 +556,10 @@ k_mc_emit(const float *__restrict__ tsdf, const int32_t *__restrict__ block_keys
             const int kth = j - (int)s_sp[row];
             const unsigned s00 = s_sign[(z + 1) * ROW_R + y + 1], s10 = s_sign[(z + 1) * ROW_R + y + 2];
             const unsigned s01 = s_sign[(z + 2) * ROW_R + y + 1], s11 = s_sign[(z + 2) * ROW_R + y + 2];
-            int64_t tbase = toff + s_r16[R16_TPREF + row];
-            unsigned before = surf;
-            int x = 0;
-            for (int q = 0; q <= kth; ++q, before &= before - 1) {     // triangles of the earlier cubes of the row
-                x = __ffs(before) - 1;
-                if (q < kth) tbase += (int)(__ldg(&MC_TRI_PACKED[cube_case(s00, s10, s01, s11, x + 1)]) >> 60);
-            }
+            const int x = (int)__fns(surf, 0, kth + 1);                // x of the row's kth surface cube
+            const unsigned below = (1u << x) - 1u;                     // the row's cubes before it: their triangle counts
+            int64_t tbase = toff + s_r16[R16_TPREF + row] + __popc(s_r16[R16_TPLANE + row] & below) +
+                            2 * __popc(s_r16[R16_TPLANE + 256 + row] & below) + 4 * __popc(s_r16[R16_TPLANE + 512 + row] & below);
             {
                 // the case's triangle list: 4-bit edge ids, three per triangle (one 64-bit load, L1-resident table)
                 unsigned long long tt = __ldg(&MC_TRI_PACKED[cube_case(s00, s10, s01, s11, x + 1)]);
@@ -638,18 +695,20 @@ k_points(const float *__restrict__ tsdf, const float *__restrict__ weight, const
 // host side
 // ------------------------------------------------------------------------------------------------
 static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
-    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    MQ3D_TRY(mq3d_grid_fresh_count(g, st));
     int64_t n = g->n_blocks_host;
     MQ3D_REQUIRE(n <= g->capacity, "internal: block count exceeds pool capacity");
     if (n > g->mc_alloc_blocks || g->mc_offsets == nullptr) {
         cudaFree(g->mc_nb); cudaFree(g->mc_emask); cudaFree(g->mc_eprefix); cudaFree(g->mc_counts); cudaFree(g->mc_offsets);
-        cudaFree(g->mc_totals);
+        cudaFree(g->mc_totals); cudaFree(g->mc_rows);
+        g->mc_rows = nullptr;
         g->mc_nb = nullptr; g->mc_emask = nullptr; g->mc_eprefix = nullptr; g->mc_counts = nullptr; g->mc_offsets = nullptr;
         g->mc_totals = nullptr;
         g->mc_alloc_blocks = 0;
         int64_t a = n + n / 4 + 16;
         MQ3D_CUDA(cudaMalloc(&g->mc_nb, sizeof(int32_t) * 27 * a));
-        MQ3D_CUDA(cudaMalloc(&g->mc_emask, sizeof(uint32_t) * SROW_WORDS * a));     // sign rows
+        MQ3D_CUDA(cudaMalloc(&g->mc_rows, sizeof(uint32_t) * 256 * a));             // (validity << 16) | sign per x-row
+        MQ3D_CUDA(cudaMalloc(&g->mc_emask, sizeof(uint32_t) * SROW_WORDS * a));     // 18-bit sign rows of the neighbourhood
         MQ3D_CUDA(cudaMalloc(&g->mc_eprefix, sizeof(uint16_t) * R16_WORDS * a));    // 16-bit row tables
         MQ3D_CUDA(cudaMalloc(&g->mc_counts, sizeof(int32_t) * 2 * a));
         MQ3D_CUDA(cudaMalloc(&g->mc_offsets, sizeof(int64_t) * 2 * (a + 1)));
@@ -661,6 +720,44 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
         k_mc_neighbors<<<(unsigned)((n * 27 + 255) / 256), 256, 0, st>>>(g->hash, g->block_keys, n, g->mc_nb);
         MQ3D_CUDA(cudaGetLastError());
     }
+    return MQ3D_OK;
+}
+
+// MQ3D_TRACE: device time of the phases of a call (CUDA events on the stream), printed to stderr
+struct MqTrace {
+    cudaStream_t st;
+    bool on;
+    int n;
+    cudaEvent_t ev[8];
+    const char *name[8];
+    explicit MqTrace(cudaStream_t s) : st(s), on(getenv("MQ3D_TRACE") != nullptr), n(0) { mark("start"); }
+    void mark(const char *what) {
+        if (!on || n >= 8) return;
+        if (cudaEventCreate(&ev[n]) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(ev[n], st);
+        name[n++] = what;
+    }
+    void report(const char *call) {     // after a stream synchronisation
+        if (!on) return;
+        fprintf(stderr, "[mq3d] %s:", call);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s %.3f ms", name[i], ms);
+        }
+        fprintf(stderr, "\n");
+    }
+    ~MqTrace() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
+};
+
+static int mc_classify(mq3d_grid *g, float weight_threshold, cudaStream_t st, MqTrace *tr = nullptr) {
+    const int64_t n = g->mc_blocks;
+    k_mc_rows<<<(unsigned)n, 256, 0, st>>>(g->tsdf, g->weight, n, weight_threshold, g->mc_rows);
+    if (tr) tr->mark("rows");
+    k_mc_classify<<<(unsigned)n, MC_CLASSIFY_THREADS, 0, st>>>(g->mc_rows, g->block_keys, g->mc_nb, n, g->part, g->mc_emask,
+                                                               g->mc_eprefix, g->mc_counts);
+    if (tr) tr->mark("classify");
+    MQ3D_CUDA(cudaGetLastError());
     return MQ3D_OK;
 }
 
@@ -696,9 +793,7 @@ extern "C" int mq3d_extract_mesh_count(mq3d_grid *g, float weight_threshold, int
     MQ3D_TRY(mc_prepare(g, st));
     int64_t n = g->mc_blocks;
     if (n > 0) {
-        k_mc_classify<<<(unsigned)n, MC_CLASSIFY_THREADS, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, n, weight_threshold, g->part,
-                                                   g->mc_emask, g->mc_eprefix, g->mc_counts);
-        MQ3D_CUDA(cudaGetLastError());
+        MQ3D_TRY(mc_classify(g, weight_threshold, st));
     }
     MQ3D_TRY(mc_finish_count(g, st, &g->mc_V, &g->mc_T));
     MQ3D_REQUIRE(g->mc_V < 2147483647LL && g->mc_T < 2147483647LL, "mesh too large for int32 indices");
@@ -722,9 +817,11 @@ extern "C" int mq3d_extract_mesh(mq3d_grid *g, float weight_threshold, float *ve
     MQ3D_TRY(mc_prepare(g, st));
     const int64_t n = g->mc_blocks;
     if (n > 0) {
-        k_mc_classify<<<(unsigned)n, MC_CLASSIFY_THREADS, 0, st>>>(g->tsdf, g->weight, g->block_keys, g->mc_nb, n, weight_threshold, g->part,
-                                                   g->mc_emask, g->mc_eprefix, g->mc_counts);
+        MqTrace tr(st);
+        tr.mark("neighbors");
+        MQ3D_TRY(mc_classify(g, weight_threshold, st, &tr));
         MQ3D_TRY(mc_scan(g, st));
+        tr.mark("scan");
         // emission is enqueued at once: the kernels read the totals on the device and do nothing if the mesh does not
         // fit -- no host round trip between classification and emission
         k_mc_emit<<<(unsigned)n, EMIT_THREADS, 0, st>>>(g->tsdf, g->block_keys, g->mc_nb, g->mc_emask, g->mc_eprefix, g->mc_counts,
@@ -734,8 +831,10 @@ extern "C" int mq3d_extract_mesh(mq3d_grid *g, float weight_threshold, float *ve
             k_mc_colors<<<(unsigned)n, EMIT_THREADS, 0, st>>>(g->tsdf, g->color, g->mc_nb, g->mc_eprefix, g->mc_counts, g->mc_offsets,
                                                               colors_dev, n, cap_vertices, cap_triangles);
         MQ3D_CUDA(cudaGetLastError());
+        tr.mark("emit");
         MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host64, g->mc_offsets + 2 * n, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, st));
         MQ3D_CUDA(cudaStreamSynchronize(st));
+        tr.report("extract_mesh");
         g->mc_V = g->pinned_host64[0];
         g->mc_T = g->pinned_host64[1];
     } else {
