@@ -212,6 +212,34 @@ int mq3d_extract_points_fill(mq3d_grid *g, float *points_dev, float *normals_dev
 int mq3d_extract_mesh_colors(mq3d_grid *g, float *colors_dev, void *stream);
 int mq3d_extract_points_colors(mq3d_grid *g, float *colors_dev, void *stream);
 
+/* ---- N1: mesh component filter on the device -------------------------------------------------
+ * Replaces filter_mesh_components (processing/reconstruction/utils/o3d_utils.py:241-321), which the reference runs
+ * on a legacy CPU mesh between marching cubes and the colour-view raycast (reconstruct_scene.py:115-118,192-195):
+ * cluster_connected_triangles (triangles sharing an edge), keep clusters with >= min_triangle_count triangles (or
+ * the largest one if none qualifies), remove_unreferenced_vertices (only if triangles were removed),
+ * remove_degenerate_triangles, remove_duplicated_triangles (equal up to rotation, first kept),
+ * remove_duplicated_vertices (identical coordinates, first kept -- this also welds the vertices that several ranks
+ * of a multi-GPU run emit on ghost edges).  Order of the surviving vertices / triangles is preserved.
+ * Inputs: vertices float32 [V][3], triangles int32 [T][3], optional per-vertex normals / colors float32 [V][3]
+ * (NULL to skip; outputs must then be NULL too).  Outputs are caller-allocated with the INPUT sizes; the valid
+ * prefix is out_n_vertices / out_n_triangles.  remove_non_manifold_edges: edges with more than two triangles are
+ * counted in info.non_manifold_edges (a marching-cubes mesh has none); if non-zero the caller completes that step.
+ * V, T > 0.  Synchronises. */
+typedef struct {
+    int64_t components;          /* connected components of the input */
+    int64_t components_kept;
+    int64_t largest_component;   /* triangles of the largest component */
+    int64_t fallback_largest;    /* 1: no component reached min_triangle_count, the largest one was kept */
+    int64_t input_triangles;
+    int64_t removed_triangles;   /* triangles of the dropped components */
+    int64_t non_manifold_edges;  /* edges of the result carried by more than two triangles */
+} mq3d_mesh_filter_info;
+int mq3d_mesh_filter(const float *vertices_dev, const float *normals_dev, const float *colors_dev, int64_t n_vertices,
+                     const int32_t *triangles_dev, int64_t n_triangles, int64_t min_triangle_count,
+                     float *out_vertices_dev, float *out_normals_dev, float *out_colors_dev,
+                     int32_t *out_triangles_dev, int64_t *out_n_vertices, int64_t *out_n_triangles,
+                     mq3d_mesh_filter_info *info, int device, void *stream);
+
 /* ---- K4: multi-view depth confidence --------------------------------------------------------
  * Replaces build_confidence_map over all reference frames of one side
  * (processing/reconstruction/confidence_estimation/estimate_depth_confidences.py:15-79 and

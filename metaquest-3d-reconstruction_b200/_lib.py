@@ -31,6 +31,7 @@ SYMBOLS = [
     "mq3d_color_resample", "mq3d_integrate_sequence_rgbx",
     "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_mesh", "mq3d_extract_points_count",
     "mq3d_extract_points_fill", "mq3d_extract_mesh_colors", "mq3d_extract_points_colors", "mq3d_confidence",
+    "mq3d_mesh_filter",
     "mq3d_scene_create", "mq3d_scene_destroy", "mq3d_scene_add_triangles",
     "mq3d_scene_create_rays_pinhole", "mq3d_scene_cast_rays",
 ]
@@ -41,6 +42,12 @@ class SeqStats(C.Structure):
                 ("blocks_loaded", C.c_int64), ("num_blocks", C.c_int64), ("batches", C.c_int64),
                 ("voxel_updates", C.c_int64), ("touch_ms", C.c_double), ("integrate_ms", C.c_double),
                 ("slow_div_batches", C.c_int64)]
+
+
+class MeshFilterInfo(C.Structure):
+    _fields_ = [("components", C.c_int64), ("components_kept", C.c_int64), ("largest_component", C.c_int64),
+                ("fallback_largest", C.c_int64), ("input_triangles", C.c_int64), ("removed_triangles", C.c_int64),
+                ("non_manifold_edges", C.c_int64)]
 
 
 class Mq3dError(RuntimeError):
@@ -98,6 +105,8 @@ def lib() -> C.CDLL:
         "mq3d_extract_mesh_colors": [vp, vp, vp],
         "mq3d_extract_points_colors": [vp, vp, vp],
         "mq3d_confidence": [vp, vp, i32, i32, i32, pf, pf, pf, i32, f64, f64, vp, vp, vp],
+        "mq3d_mesh_filter": [vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64),
+                             C.POINTER(MeshFilterInfo), i32, vp],
         "mq3d_scene_create": [i32, C.POINTER(vp)],
         "mq3d_scene_destroy": [vp],
         "mq3d_scene_add_triangles": [vp, vp, i64, vp, i64, vp],

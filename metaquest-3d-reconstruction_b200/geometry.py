@@ -14,13 +14,73 @@ import torch
 
 
 class LegacyTriangleMesh:
-    """Stand-in for o3d.geometry.TriangleMesh (float64 vertices, int32 triangles)."""
+    """Stand-in for o3d.geometry.TriangleMesh (float64 vertices, int32 triangles) with the methods the reference's
+    filter_mesh_components calls (o3d_utils.py:258-301), implemented on the host in meshops.py."""
 
     def __init__(self, vertices=None, triangles=None, vertex_normals=None, vertex_colors=None):
         self.vertices = np.zeros((0, 3)) if vertices is None else np.asarray(vertices, dtype=np.float64)
         self.triangles = np.zeros((0, 3), np.int32) if triangles is None else np.asarray(triangles, dtype=np.int32)
         self.vertex_normals = None if vertex_normals is None else np.asarray(vertex_normals, dtype=np.float64)
         self.vertex_colors = None if vertex_colors is None else np.asarray(vertex_colors, dtype=np.float64)
+
+    # -- Open3D legacy TriangleMesh methods ------------------------------------------------------------
+    def has_triangles(self) -> bool:
+        return len(self.triangles) > 0
+
+    def cluster_connected_triangles(self):
+        """(cluster index per triangle, triangles per cluster, area per cluster); triangles sharing an edge are
+        connected, clusters are numbered by their lowest triangle index."""
+        from . import meshops
+        t = self.triangles.astype(np.int64)
+        if len(t) == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0)
+        label, counts = meshops.cluster_connected_triangles(t)
+        area = np.bincount(label, weights=meshops.triangle_areas(self.vertices, t), minlength=len(counts))
+        return label, counts, area
+
+    def remove_triangles_by_mask(self, mask):
+        mask = np.asarray(mask, bool)
+        if len(mask) != len(self.triangles):
+            raise RuntimeError("remove_triangles_by_mask: mask length does not match the number of triangles")
+        self.triangles = self.triangles[~mask]
+        return self
+
+    def _set(self, v, attrs, t):
+        self.vertices, self.triangles = np.asarray(v, np.float64), np.asarray(t, np.int32).reshape(-1, 3)
+        self.vertex_normals, self.vertex_colors = attrs
+
+    def remove_unreferenced_vertices(self):
+        from . import meshops
+        used = np.zeros(len(self.vertices), bool)
+        used[self.triangles.ravel()] = True
+        self._set(*meshops.compact_vertices(self.vertices, [self.vertex_normals, self.vertex_colors],
+                                            self.triangles.astype(np.int64), used))
+        return self
+
+    def remove_degenerate_triangles(self):
+        from . import meshops
+        self.triangles = meshops.remove_degenerate_triangles(self.triangles)
+        return self
+
+    def remove_duplicated_triangles(self):
+        from . import meshops
+        self.triangles = meshops.remove_duplicated_triangles(self.triangles)
+        return self
+
+    def remove_duplicated_vertices(self):
+        from . import meshops
+        self._set(*meshops.remove_duplicated_vertices(self.vertices, [self.vertex_normals, self.vertex_colors],
+                                                      self.triangles.astype(np.int64)))
+        return self
+
+    def remove_non_manifold_edges(self):
+        from . import meshops
+        self.triangles = meshops.remove_non_manifold_edges(self.vertices, self.triangles.astype(np.int64)).astype(np.int32)
+        return self
+
+    @staticmethod
+    def create_coordinate_frame(size=1.0, origin=(0, 0, 0)):
+        raise RuntimeError("interactive visualisation helpers are outside the hot-path build")
 
 
 class LegacyPointCloud:

@@ -174,114 +174,66 @@ def estimate_depth_confidences(depth_data_io, config, device="CUDA:0", save: boo
     return out
 
 
-def _cluster_connected_triangles(t: np.ndarray):
-    """Open3D TriangleMesh::ClusterConnectedTriangles: triangles that share an (undirected) EDGE belong to one
-    cluster; clusters are numbered by their lowest triangle index.  Returns (cluster id per triangle, sizes)."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
-    n = len(t)
-    e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
-    tri = np.tile(np.arange(n), 3)
-    order = np.lexsort((e[:, 1], e[:, 0]))
-    e, tri = e[order], tri[order]
-    same = (e[1:] == e[:-1]).all(1)                       # consecutive entries of one edge: link their triangles
-    g = coo_matrix((np.ones(int(same.sum()), np.int8), (tri[:-1][same], tri[1:][same])), shape=(n, n))
-    _, label = connected_components(g, directed=False)
-    return label, np.bincount(label)
-
-
-def _remove_non_manifold_edges(v: np.ndarray, t: np.ndarray) -> np.ndarray:
-    """Open3D TriangleMesh::RemoveNonManifoldEdges: while an edge has more than two triangles, delete its
-    smallest-area triangles until two are left (edges visited in sorted order; Open3D's order is that of an
-    unordered_map)."""
-    while len(t):
-        e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
-        tri = np.tile(np.arange(len(t)), 3)
-        order = np.lexsort((e[:, 1], e[:, 0]))
-        e, tri = e[order], tri[order]
-        start = np.concatenate([[True], (e[1:] != e[:-1]).any(1)])
-        group = np.cumsum(start) - 1
-        size = np.bincount(group)
-        bad = np.nonzero(size > 2)[0]
-        if len(bad) == 0:
-            break
-        p = v[t].astype(np.float64)
-        area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
-        first = np.nonzero(start)[0]
-        for gi in bad:
-            members = tri[first[gi]: first[gi] + size[gi]]
-            alive = members[area[members] > 0]
-            for _ in range(len(alive) - 2):
-                alive = members[area[members] > 0]
-                area[alive[np.argmin(area[alive])]] = -1.0
-        if not (area < 0).any():
-            break                                          # only zero-area triangles left on the edge
-        t = t[area >= 0]
-    return t
-
-
-def filter_mesh_components(mesh: TriangleMesh, min_triangle_count: int = 2000) -> TriangleMesh:
+def filter_mesh_components(mesh: TriangleMesh, min_triangle_count: int = 2000, backend: str = "auto") -> TriangleMesh:
     """Drop-in for o3d_utils.filter_mesh_components (:241-321), step for step on the legacy-mesh semantics of
     Open3D: cluster_connected_triangles (edge adjacency), keep clusters with >= min_triangle_count triangles (or
     the largest one), remove_unreferenced_vertices (only if something was removed), remove_degenerate_triangles
     (repeated vertex index), remove_duplicated_triangles (equal up to rotation), remove_duplicated_vertices
     (identical coordinates; first occurrence kept, which also welds the vertices several ranks re-emit on
-    ghost edges) and remove_non_manifold_edges.  Normals and colours follow their vertices.  Host-side
-    (NumPy / SciPy); SURVEY 8f N1 ranks a device version next."""
-    v = mesh.vertex.positions.detach().cpu().numpy()
-    t = mesh.triangle.indices.detach().cpu().numpy().astype(np.int64)
-    attrs = [None if a is None else a.detach().cpu().numpy() for a in (mesh.vertex.normals, mesh.vertex.colors)]
-    if len(t) == 0:
+    ghost edges) and remove_non_manifold_edges.  Normals and colours follow their vertices.
+
+    backend "device": the whole chain on the GPU (mq3d_mesh_filter: sort-based edge adjacency + pointer-jumping
+    union-find, compaction, coordinate weld -- no D2H / H2D round trip of the mesh); "host": the NumPy / SciPy
+    implementation in meshops.py (the checker); "auto": device for CUDA meshes."""
+    if int(mesh.triangle.indices.shape[0]) == 0:
         print("[Warning] Mesh filtering: Input mesh has no triangles, returning as-is")
         return mesh
-    original = len(t)
-    tlabel, counts = _cluster_connected_triangles(t)
-    valid = np.nonzero(counts >= min_triangle_count)[0]
-    if len(valid) == 0:
+    if backend == "auto":
+        backend = "device" if mesh.vertex.positions.is_cuda else "host"
+    if backend == "device":
+        from .meshfilter import filter_mesh_components_device
+        out, info = filter_mesh_components_device(mesh, min_triangle_count)
+    else:
+        out, info = _filter_mesh_components_host(mesh, min_triangle_count)
+    n_comp, n_valid, removed_tris, original, final, largest, fallback = info
+    if fallback:
         print(f"[Warning] Mesh filtering: No components have >= {min_triangle_count} triangles. "
-              f"Largest component has {counts.max()} triangles.")
+              f"Largest component has {largest} triangles.")
         print("[Warning] Mesh filtering: Returning largest component only.")
-        valid = np.array([np.argmax(counts)])
-    keep = np.isin(tlabel, valid)
-    removed_tris = int(original - keep.sum())
-
-    def compact(v, attrs, t, used):                        # drop the vertices not flagged in `used`
-        remap = np.cumsum(used) - 1
-        return v[used], [None if a is None else a[used] for a in attrs], remap[t]
-
-    if removed_tris > 0:
-        t = t[keep]
-        used = np.zeros(len(v), bool)
-        used[t.ravel()] = True
-        v, attrs, t = compact(v, attrs, t, used)           # remove_unreferenced_vertices
-    t = t[(t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2])]          # degenerate
-    if len(t):                                             # duplicated: equal after rotating the smallest index first
-        k = np.argmin(t, axis=1)
-        rot = np.stack([np.take_along_axis(t, ((k + i) % 3)[:, None], 1)[:, 0] for i in range(3)], axis=1)
-        _, first = np.unique(rot, axis=0, return_index=True)
-        t = t[np.sort(first)]
-    if len(v):                                             # duplicated vertices: identical coordinates
-        _, first, inverse = np.unique(v, axis=0, return_index=True, return_inverse=True)
-        inverse = np.asarray(inverse).reshape(-1)
-        if len(first) != len(v):
-            keep_v = np.zeros(len(v), bool)
-            keep_v[first] = True
-            new_index = (np.cumsum(keep_v) - 1)[first][inverse]      # old vertex -> index of its first occurrence
-            v, attrs, t = v[keep_v], [None if a is None else a[keep_v] for a in attrs], new_index[t]
-    t = _remove_non_manifold_edges(v, t)
-    removed = len(counts) - len(valid)
+    removed = n_comp - n_valid
     if removed > 0:
-        print(f"[Info] Mesh filtering: Found {len(counts)} connected component(s)")
+        print(f"[Info] Mesh filtering: Found {n_comp} connected component(s)")
         print(f"[Info] Mesh filtering: Removed {removed} small component(s) with < {min_triangle_count} triangles")
         print(f"[Info] Mesh filtering: Removed {removed_tris} triangles from small components")
-        print(f"[Info] Mesh filtering: Kept {len(valid)} component(s) with >= {min_triangle_count} triangles")
-        print(f"[Info] Mesh filtering: Final mesh has {len(t)} triangles (was {original})")
+        print(f"[Info] Mesh filtering: Kept {n_valid} component(s) with >= {min_triangle_count} triangles")
+        print(f"[Info] Mesh filtering: Final mesh has {final} triangles (was {original})")
     else:
-        print(f"[Info] Mesh filtering: All {len(counts)} component(s) have >= {min_triangle_count} triangles, "
+        print(f"[Info] Mesh filtering: All {n_comp} component(s) have >= {min_triangle_count} triangles, "
               f"no filtering needed")
-    dev = mesh.device
-    up = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
-    return TriangleMesh(up(v, torch.float32), up(t, torch.int32), up(attrs[0], torch.float32), up(attrs[1], torch.float32))
+    return out
+
+
+def _filter_mesh_components_host(mesh: TriangleMesh, min_triangle_count: int):
+    """The reference's chain on a legacy mesh (geometry.LegacyTriangleMesh implements Open3D's methods on the host)."""
+    legacy = mesh.to_legacy()
+    clusters, counts, _ = legacy.cluster_connected_triangles()
+    clusters, counts = np.asarray(clusters), np.asarray(counts)
+    original = len(clusters)
+    valid = np.nonzero(counts >= min_triangle_count)[0]
+    fallback = len(valid) == 0
+    if fallback:
+        valid = np.array([np.argmax(counts)])
+    keep = np.isin(clusters, valid)
+    removed_tris = int(original - keep.sum())
+    if removed_tris > 0:
+        legacy.remove_triangles_by_mask(~keep)
+        legacy.remove_unreferenced_vertices()
+    legacy.remove_degenerate_triangles()
+    legacy.remove_duplicated_triangles()
+    legacy.remove_duplicated_vertices()
+    legacy.remove_non_manifold_edges()
+    out = TriangleMesh.from_legacy(legacy, device=mesh.device)
+    return out, (len(counts), len(valid), removed_tris, original, len(legacy.triangles), int(counts.max()), fallback)
 
 
 def raycast_in_color_view(scene: RaycastingScene, dataset: CameraDataset) -> Generator[np.ndarray, None, None]:

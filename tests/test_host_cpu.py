@@ -145,7 +145,8 @@ def _mesh(v, t, with_attrs=True):
 def test_filter_mesh_components_follows_open3d_legacy_semantics(capsys):
     """filter_mesh_components (o3d_utils.py:241-321) on CPU tensors: edge-adjacency clusters, size threshold with the
     largest-cluster fallback, degenerate / duplicated triangle removal, vertex welding, non-manifold edges."""
-    from mq3d_b200.ops import _cluster_connected_triangles, filter_mesh_components
+    from mq3d_b200.meshops import cluster_connected_triangles as _cluster_connected_triangles
+    from mq3d_b200.ops import filter_mesh_components
     # two tetrahedra that share ONE VERTEX only (same index): edge adjacency keeps them apart
     va, ta = _tetra((0, 0, 0))
     vb, tb = _tetra((0, 0, 0), scale=-1.0)
