@@ -240,6 +240,17 @@ int mq3d_mesh_filter(const float *vertices_dev, const float *normals_dev, const 
                      int32_t *out_triangles_dev, int64_t *out_n_vertices, int64_t *out_n_triangles,
                      mq3d_mesh_filter_info *info, int device, void *stream);
 
+/* ---- N4: odometry information matrix -----------------------------------------------------------
+ * Replaces o3d.t.pipelines.odometry.compute_odometry_information_matrix(source_depth, target_depth, intrinsic,
+ * source_to_target, dist_threshold, depth_scale, depth_max) as build_pose_graph_for_fragment calls it for every
+ * consecutive frame pair and every overlapping key-frame pair
+ * (processing/reconstruction/depth_optimization/make_fragments.py:142-150,228-233).  Depth images float32 [H][W]
+ * on the device; K row-major double[9], source_to_target row-major double[16] (host).  info_out: host double[36],
+ * row-major symmetric 6 x 6 (rotation block first).  Synchronises. */
+int mq3d_odometry_information(const float *source_depth_dev, const float *target_depth_dev, int width, int height,
+                              const double K[9], const double source_to_target[16], float dist_threshold,
+                              float depth_scale, float depth_max, double info_out[36], int device, void *stream);
+
 /* ---- K4: multi-view depth confidence --------------------------------------------------------
  * Replaces build_confidence_map over all reference frames of one side
  * (processing/reconstruction/confidence_estimation/estimate_depth_confidences.py:15-79 and

@@ -31,7 +31,7 @@ SYMBOLS = [
     "mq3d_color_resample", "mq3d_integrate_sequence_rgbx",
     "mq3d_extract_mesh_count", "mq3d_extract_mesh_fill", "mq3d_extract_mesh", "mq3d_extract_points_count",
     "mq3d_extract_points_fill", "mq3d_extract_mesh_colors", "mq3d_extract_points_colors", "mq3d_confidence",
-    "mq3d_mesh_filter",
+    "mq3d_mesh_filter", "mq3d_odometry_information",
     "mq3d_scene_create", "mq3d_scene_destroy", "mq3d_scene_add_triangles",
     "mq3d_scene_create_rays_pinhole", "mq3d_scene_cast_rays",
 ]
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "mq3d_extract_mesh_colors": [vp, vp, vp],
         "mq3d_extract_points_colors": [vp, vp, vp],
         "mq3d_confidence": [vp, vp, i32, i32, i32, pf, pf, pf, i32, f64, f64, vp, vp, vp],
+        "mq3d_odometry_information": [vp, vp, i32, i32, pd, pd, f32, f32, f32, pd, i32, vp],
         "mq3d_mesh_filter": [vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64),
                              C.POINTER(MeshFilterInfo), i32, vp],
         "mq3d_scene_create": [i32, C.POINTER(vp)],

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libmq3d.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
 SOURCES = ["mq3d_grid.cu", "mq3d_depth.cu", "mq3d_integrate.cu", "mq3d_mesh.cu", "mq3d_confidence.cu",
-           "mq3d_raycast.cu", "mq3d_peer.cu", "mq3d_meshfilter.cu"]
+           "mq3d_raycast.cu", "mq3d_peer.cu", "mq3d_meshfilter.cu", "mq3d_odometry.cu"]
 HEADERS = ["mq3d_common.cuh", "mc_tables.h", os.path.join("..", "..", "include", "mq3d.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

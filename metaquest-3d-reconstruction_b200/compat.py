@@ -168,6 +168,42 @@ class Tensor:
     def __getitem__(self, k):
         return Tensor(self.torch[k])
 
+    def item(self):
+        return self.torch.item()
+
+    def __float__(self):
+        return float(self.torch)
+
+    def __truediv__(self, o):
+        return Tensor(self.torch / _un(o))
+
+    def __mul__(self, o):
+        return Tensor(self.torch * _un(o))
+
+    def __add__(self, o):
+        return Tensor(self.torch + _un(o))
+
+    def __sub__(self, o):
+        return Tensor(self.torch - _un(o))
+
+    def __matmul__(self, o):
+        return Tensor(self.torch @ _un(o))
+
+    def __gt__(self, o):
+        return Tensor(self.torch > _un(o))
+
+    def __lt__(self, o):
+        return Tensor(self.torch < _un(o))
+
+    def __ge__(self, o):
+        return Tensor(self.torch >= _un(o))
+
+    def __le__(self, o):
+        return Tensor(self.torch <= _un(o))
+
+    def __bool__(self):
+        return bool(self.torch)
+
     def __getattr__(self, name):
         # anything else (is_cuda, detach, ...) is answered by the torch tensor underneath
         if name == "torch" or name.startswith("__"):
@@ -385,6 +421,15 @@ def _np(x):
     return x.numpy() if isinstance(x, Tensor) else np.asarray(x)
 
 
+def _odometry_information(source_depth, target_depth, intrinsic, source_to_target, dist_threshold=0.07, depth_scale=1000.0,
+                          depth_max=3.0):
+    """o3d.t.pipelines.odometry.compute_odometry_information_matrix -> 6x6 Float64 Tensor on the host."""
+    from . import ops
+    return Tensor(torch.from_numpy(ops.compute_odometry_information_matrix(source_depth, target_depth, _np(intrinsic),
+                                                                           _np(source_to_target), dist_threshold,
+                                                                           depth_scale, depth_max)))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # o3d.utility, o3d.pipelines.registration, o3d.camera: value containers
 # ---------------------------------------------------------------------------------------------------------
@@ -483,7 +528,9 @@ t = _Namespace("t",
                io=_Namespace("t.io", write_point_cloud=_write_pcd, write_triangle_mesh=_write_mesh,
                              read_triangle_mesh=lambda f, *a, **k: TriangleMesh.from_legacy(_read_mesh_legacy(f)),
                              read_point_cloud=lambda filename, *a, **k: PointCloud.from_legacy(_read_pcd_legacy(filename))),
-               pipelines=_Namespace("t.pipelines"))
+               pipelines=_Namespace("t.pipelines",
+                                    odometry=_Namespace("t.pipelines.odometry",
+                                                        compute_odometry_information_matrix=_odometry_information)))
 geometry = _Namespace("geometry", TriangleMesh=_geom.LegacyTriangleMesh, PointCloud=_geom.LegacyPointCloud)
 utility = _Namespace("utility", Vector3dVector=Vector3dVector, Vector3iVector=Vector3iVector)
 pipelines = _Namespace("pipelines",

@@ -137,6 +137,39 @@ def integrate_fragment_point_cloud(depth_data_io, frag_dataset: DepthDataset, si
         return None
 
 
+def compute_odometry_information_matrix(source_depth, target_depth, intrinsic, source_to_target, dist_threshold: float = 0.07,
+                                        depth_scale: float = 1000.0, depth_max: float = 3.0) -> np.ndarray:
+    """Drop-in for o3d.t.pipelines.odometry.compute_odometry_information_matrix as build_pose_graph_for_fragment calls
+    it (depth_optimization/make_fragments.py:142-150,228-233): float64 [6,6] information matrix of the
+    point-to-point residuals between two depth frames under `source_to_target`.  Depth frames: float32 [H,W] CUDA
+    tensors (or Images / arrays, moved to the device of the source frame); intrinsic 3x3 and source_to_target 4x4 on
+    the host.  The pose-graph optimisation consuming the edges stays out of scope."""
+    import ctypes as C
+    from . import _lib
+    from .vbg import _as_np, _stream, as_depth_tensor
+    src = source_depth
+    for attr in ("as_tensor", ):
+        if hasattr(src, attr):
+            src = src.as_tensor()
+    src = src.torch if hasattr(src, "torch") else src
+    if isinstance(src, np.ndarray):
+        src = torch.from_numpy(np.ascontiguousarray(src))
+    dev = src.device if src.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    s = as_depth_tensor(source_depth, dev)
+    t = as_depth_tensor(target_depth, dev)
+    if s.shape != t.shape:
+        raise RuntimeError(f"source and target depth differ in shape: {tuple(s.shape)} vs {tuple(t.shape)}")
+    H, W = s.shape
+    K = _as_np(intrinsic, np.float64, (3, 3))
+    T = _as_np(source_to_target, np.float64, (4, 4))
+    info = np.zeros((6, 6), np.float64)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mq3d_odometry_information(_lib.dptr(s), _lib.dptr(t), W, H, _lib.darr(K), _lib.darr(T),
+                                                        C.c_float(dist_threshold), C.c_float(depth_scale),
+                                                        C.c_float(depth_max), _lib.darr(info), int(dev.index or 0), _stream()))
+    return info
+
+
 def estimate_depth_confidences(depth_data_io, config, device="CUDA:0", save: bool = True) -> dict:
     """Drop-in for estimate_depth_confidences (estimate_depth_confidences.py:120-154): one K4 launch per
     side instead of a process pool.  Writes `<side>_depth_confidence/<ts>.npz` (keys confidence_map f64,

@@ -269,3 +269,45 @@ def extract_points(grid: dict, voxel_size, weight_threshold):
             norms.append(np.stack([n3[a] / norm for a in range(3)], axis=1))
             pkeys.append(np.stack([gx[m], gy[m], gz[m], np.full(m.sum(), e, np.int32)], axis=1))
     return np.concatenate(pts), np.concatenate(norms), np.concatenate(pkeys).astype(np.int32)
+
+
+def odometry_information(source_depth, target_depth, K, T, dist_threshold, depth_scale, depth_max):
+    """Independent dense restatement of compute_odometry_information_matrix: float32 geometry as
+    Open3D's vertex maps and TransformIndexer, float64 accumulation.  Returns float64 [6,6]."""
+    f32 = np.float32
+    H, W = source_depth.shape
+    fx, fy, cx, cy = f32(K[0][0]), f32(K[1][1]), f32(K[0][2]), f32(K[1][2])
+    R, t = np.asarray(T, np.float64)[:3, :3].astype(f32), np.asarray(T, np.float64)[:3, 3].astype(f32)
+
+    def vertex_map(depth):
+        d = (depth.astype(f32) / f32(depth_scale)).astype(f32)
+        ok = (d > 0) & (d < f32(depth_max))
+        u, v = np.meshgrid(np.arange(W, dtype=f32), np.arange(H, dtype=f32))
+        x = ((u - cx) * d / fx).astype(f32)
+        y = ((v - cy) * d / fy).astype(f32)
+        return np.stack([x, y, d], -1), ok
+    sv, sok = vertex_map(source_depth)
+    tv, tok = vertex_map(target_depth)
+    q = np.stack([(R[i, 0] * sv[..., 0] + R[i, 1] * sv[..., 1]).astype(f32) for i in range(3)], -1)
+    q = np.stack([((q[..., i] + R[i, 2] * sv[..., 2]).astype(f32) + t[i]).astype(f32) for i in range(3)], -1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv_z = (f32(1.0) / q[..., 2]).astype(f32)
+        u = np.round(((fx * q[..., 0]).astype(f32) * inv_z + cx).astype(f32))
+        v = np.round(((fy * q[..., 1]).astype(f32) * inv_z + cy).astype(f32))
+    # np.round is half-to-even, roundf is half-away-from-zero: redo the ties
+    with np.errstate(divide="ignore", invalid="ignore"):
+        uf = ((fx * q[..., 0]).astype(f32) * inv_z + cx).astype(f32)
+        vf = ((fy * q[..., 1]).astype(f32) * inv_z + cy).astype(f32)
+    u = np.where(np.isfinite(uf), np.sign(uf) * np.floor(np.abs(uf) + f32(0.5)), uf)
+    v = np.where(np.isfinite(vf), np.sign(vf) * np.floor(np.abs(vf) + f32(0.5)), vf)
+    ok = sok & ~(q[..., 2] < 0) & (u >= 0) & (v >= 0) & (u <= W - 1) & (v <= H - 1)
+    ui, vi = np.where(ok, u, 0).astype(np.int64), np.where(ok, v, 0).astype(np.int64)
+    ok &= tok[vi, ui]
+    r = (q - tv[vi, ui]).astype(f32)
+    r2 = ((r[..., 0] * r[..., 0] + r[..., 1] * r[..., 1]).astype(f32) + r[..., 2] * r[..., 2]).astype(f32)
+    ok &= r2 <= f32(dist_threshold) * f32(dist_threshold)
+    p = q[ok].astype(np.float64)
+    z, o = np.zeros(len(p)), np.ones(len(p))
+    J = np.stack([np.stack([z, p[:, 2], -p[:, 1], o, z, z], 1), np.stack([-p[:, 2], z, p[:, 0], z, o, z], 1),
+                  np.stack([p[:, 1], -p[:, 0], z, z, z, o], 1)], 1)       # [n,3,6]
+    return np.einsum("nki,nkj->ij", J, J)

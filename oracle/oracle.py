@@ -228,3 +228,14 @@ def cast_rays(verts, tris, rays):
     lib().orc_cast_rays(_p(verts), C.c_int64(len(verts)), _p(tris), C.c_int64(len(tris)), _p(rays),
                         C.c_int64(out.size), _p(out))
     return out
+
+
+def odometry_information(source_depth, target_depth, K, source_to_target, dist_threshold, depth_scale, depth_max):
+    """o3d.t.pipelines.odometry.compute_odometry_information_matrix (make_fragments.py:142-150): float64 [6,6]."""
+    s, t = _f32(source_depth), _f32(target_depth)
+    H, W = s.shape
+    info = np.zeros((6, 6), np.float64)
+    lib().orc_odometry_information(_p(s), _p(t), C.c_int(W), C.c_int(H), _p(_f64(K).reshape(9)),
+                                   _p(_f64(source_to_target).reshape(16)), C.c_float(dist_threshold), C.c_float(depth_scale),
+                                   C.c_float(depth_max), _p(info))
+    return info

@@ -102,3 +102,22 @@ def test_raycast_plane_and_empty_scene(cuda_device):
     assert np.allclose(t, 2.0, atol=1e-6)
     empty = RaycastingScene(device=cuda_device)
     assert np.isinf(empty.cast_rays(rays)["t_hit"].cpu().numpy()).all()
+
+
+def test_odometry_information_matches_oracle(cuda_device, oracle):
+    """N4: mq3d_odometry_information against the oracle on consecutive frames and on a key-frame pair of a synthetic
+    sequence (same correspondences; float64 sums agree to rounding of the summation order)."""
+    from helpers import capture, pipeline_cameras
+    from mq3d_b200.ops import compute_odometry_information_matrix
+    cap = capture(12)
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    ds = cap.dataset
+    lin = [oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i]) for i in range(12)]
+    for i, j in ((0, 1), (3, 4), (0, 10)):
+        T = Ewc[j].astype(np.float64) @ Ecw[i].astype(np.float64)
+        want = oracle.odometry_information(lin[i], lin[j], K[0], T, 0.07, 1.0, 4.0)
+        got = compute_odometry_information_matrix(torch.from_numpy(lin[i]).to(cuda_device), torch.from_numpy(lin[j]).to(cuda_device),
+                                                  K[0], T, dist_threshold=0.07, depth_scale=1.0, depth_max=4.0)
+        assert got.shape == (6, 6) and got.dtype == np.float64 and want[5, 5] > 1000
+        assert got[5, 5] == want[5, 5]                                  # the same pixels correspond
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-6)

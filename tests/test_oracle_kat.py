@@ -308,3 +308,36 @@ def test_edge_cases_empty_ragged_extreme(oracle):
     lin = oracle.depth_to_linear(np.array([[1.0, 0.5, 0.0]], np.float32), 0.1, np.inf)
     # d = 1 (far plane at infinity) maps to 0 = "no measurement", d = 0 to the near plane (depth_utils.py:42-46)
     assert lin[0, 0] == 0 and lin[0, 1] == np.float32(0.2) and lin[0, 2] == np.float32(0.1)
+
+
+def test_odometry_information_known_answers(oracle):
+    """compute_odometry_information_matrix (make_fragments.py:142-150).  Identical frames under the
+    identity: every valid pixel matches itself, so the translation block is n * I and the rotation block is
+    sum(|p|^2 I - p p^T); a distance threshold below the residual leaves nothing; the independent NumPy restatement
+    agrees on real frames under a real relative pose."""
+    from oracle import numpy_mirror as mirror
+    H = W = 24
+    K = np.array([[20.0, 0, 12.0], [0, 20.0, 12.0], [0, 0, 1.0]])
+    rng = np.random.default_rng(5)
+    d = (1.0 + rng.random((H, W))).astype(np.float32)
+    d[3, 4] = 0.0            # invalid: clipped
+    d[5, 6] = 9.0            # beyond depth_max: clipped
+    info = oracle.odometry_information(d, d, K, np.eye(4), 0.07, 1.0, 4.0)
+    n = H * W - 2
+    assert np.allclose(info[3:, 3:], n * np.eye(3)) and np.allclose(info, info.T)
+    u, v = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    ok = (d > 0) & (d < 4.0)
+    p = np.stack([(u - 12.0) * d / 20.0, (v - 12.0) * d / 20.0, d], -1)[ok].astype(np.float64)
+    want = (p * p).sum() * np.eye(3) - p.T @ p
+    assert np.allclose(info[:3, :3], want, rtol=1e-6)
+    # a 10 cm offset along z with a 7 cm threshold: no correspondence survives; with 20 cm all do
+    T = np.eye(4)
+    T[2, 3] = 0.10
+    flat = np.full((H, W), 2.0, np.float32)
+    assert not oracle.odometry_information(flat, flat, K, T, 0.07, 1.0, 4.0).any()
+    far = oracle.odometry_information(flat, flat, K, T, 0.20, 1.0, 4.0)
+    assert far[3, 3] > 0.8 * H * W and far[3, 3] == far[4, 4] == far[5, 5]
+    # depth_scale divides before the clip
+    assert np.allclose(oracle.odometry_information(d * 1000, d * 1000, K, np.eye(4), 0.07, 1000.0, 4.0), info, rtol=1e-6)
+    a = mirror.odometry_information(d, d, K, np.eye(4), 0.07, 1.0, 4.0)      # float64 products there, float32 here
+    assert np.allclose(a, info, rtol=1e-5, atol=1e-3) and a[5, 5] == info[5, 5]

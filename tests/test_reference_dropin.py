@@ -203,6 +203,43 @@ def test_reference_integrate_and_raycast_unmodified(ref, cuda_device, oracle, tm
 
 @needs_reference
 @pytest.mark.gpu
+def test_reference_fragment_pose_graph_unmodified(ref, cuda_device, oracle, tmp_path):
+    """depth_optimization.make_fragments.build_pose_graph_for_fragment (:83-240) -- load_depth_map on the device,
+    o3d.t.pipelines.odometry.compute_odometry_information_matrix per consecutive pair and per overlapping key-frame
+    pair, PoseGraph / PoseGraphNode / PoseGraphEdge -- runs unmodified on the stand-in; every edge's
+    information matrix equals the oracle's.  The pose-graph optimisation that would follow is out of scope."""
+    from helpers import pipeline_cameras
+    from mq3d_b200 import synth
+    from mq3d_b200.models import Side
+    o3d = ref["open3d"]
+    mf = ref["processing.reconstruction.depth_optimization.make_fragments"]
+    cfg_mod = ref["config.reconstruction_config"]
+    side_mod = importlib.import_module("models.side")
+    tr_mod = importlib.import_module("models.transforms")
+    caps = synth.write_project(tmp_path, 12, sides=(Side.LEFT,), width=160, height=160)
+    data_io = ref["dataio.data_io"].DataIO(project_dir=tmp_path)
+    ds = data_io.depth.load_depth_dataset(side=side_mod.Side.LEFT, use_cache=False)
+    ds.transforms = ds.transforms.convert_coordinate_system(target_coordinate_system=tr_mod.CoordinateSystem.OPEN3D,
+                                                            is_camera=True)
+    cfg = cfg_mod.FragmentGenerationConfig(device=o3d.core.Device("CUDA:0"))
+    cfg.use_confidence_filtered_depth = False
+    cfg.depth_max, cfg.odometry_loop_interval, cfg.dist_threshold = 4.0, 5, 0.07
+    pg = mf.build_pose_graph_for_fragment(frag_dataset=ds, depth_data_io=data_io.depth, side=side_mod.Side.LEFT, config=cfg)
+    assert len(pg.nodes) == 12 and len(pg.edges) >= 11
+    cap = caps[Side.LEFT]
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    lin = [oracle.depth_to_linear(cap.raw[i], cap.dataset.nears[i], cap.dataset.fars[i]) for i in range(12)]
+    for e in pg.edges:
+        i, j = e.source_node_id, e.target_node_id
+        want = oracle.odometry_information(lin[i], lin[j], K[0], np.asarray(e.transformation, np.float64), 0.07, 1.0, 4.0)
+        assert e.information.shape == (6, 6) and np.allclose(e.information, want, rtol=1e-9, atol=1e-6), (i, j)
+        assert e.uncertain == (j != i + 1)
+    with pytest.raises(RuntimeError, match="outside the B200 hot-path build"):
+        mf.optimize_dataset_pose(data_io.depth, ds, side_mod.Side.LEFT, cfg)
+
+
+@needs_reference
+@pytest.mark.gpu
 def test_reference_stage_driver_unmodified(ref, cuda_device, tmp_path, capsys):
     """processing.reconstruction.reconstruct_scene.reconstruct_scene -- the reference's stage driver -- runs end to
     end on the stand-in: datasets, integrate LEFT then RIGHT into one grid, colorless_vbg.npz, colourless point
