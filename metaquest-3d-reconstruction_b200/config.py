@@ -93,6 +93,10 @@ class IntegrationConfig:
     block_count: int = 50_000
     depth_max: float = 1.5
     trunc_voxel_multiplier: float = 8.0
+    # extensions of this build (absent from the reference's YAML, so defaults keep its behaviour):
+    integrate_color: bool = False   # colour attribute + Open3D's colour Integrate overload (north-star row A3c): every depth
+                                    # frame takes the colour frame nearest in time of the same eye; writes color_mesh.ply
+    batch_frames: int = 256         # frames per block residency of the fused integrate kernel (<= 256)
 
 
 @dataclass

@@ -9,6 +9,7 @@ host buffer, validates all frames with K1's fused reduction on the GPU and keeps
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -66,6 +67,16 @@ class DepthDataIO:
         return self.confidence_dir(side).exists()
 
     # -- raw frames -------------------------------------------------------------------------------------
+    RAW_CACHE_BUDGET_BYTES = int(os.environ.get("MQ3D_RAW_CACHE_MB", "2048")) << 20
+
+    def has_raw_cache(self, side, dataset: DepthDataset) -> bool:
+        """True when every frame of `dataset` is still in memory from `build_depth_dataset` (small captures)."""
+        cached = self._raw_cache.get(side)
+        if cached is None or len(cached[0]) == 0:
+            return False
+        have = set(int(t) for t in cached[0])
+        return all(int(t) in have for t in dataset.timestamps)
+
     def load_raw_depth_map(self, side, timestamp, width, height) -> Optional[np.ndarray]:
         """`<ts>.raw` little-endian float32 [H,W] (depth_data_io.py:41-46), or None if missing."""
         p = self.depth_map_path(side, timestamp)
@@ -180,20 +191,30 @@ class DepthDataIO:
         keep = np.zeros(n, bool)
         raws = None
         if n:
+            # every file is read ONCE, through the bounded ring of ingest.RawDepthStreamer; is_depth_map_valid runs as
+            # K1's fused reduction on the device chunk by chunk; the frames are kept in memory for integrate() only
+            # when the whole side fits the cache budget (MQ3D_RAW_CACHE_MB, default 2 GiB)
+            from .ingest import RawDepthStreamer
             H, W = rows[0][2], rows[0][1]
-            raws = np.zeros((n, H, W), np.float32)
-            for i, (ts, w, h, _) in enumerate(rows):
+            for ts, w, h, _ in rows:
                 if (w, h) != (W, H):
                     raise RuntimeError("all depth frames of a side must share one resolution")
-                raws[i] = np.fromfile(self.depth_map_path(side, ts), dtype="<f4").reshape(H, W)
             dev = torch.device("cuda", torch.cuda.current_device())
             nears = np.array([float(r["near_z"]) for *_, r in rows])
             fars = np.array([float(r["far_z"]) for *_, r in rows])
-            _, valid = depth_prepare(torch.from_numpy(raws).pin_memory().to(dev, non_blocking=True), nears, fars)
-            keep = valid.cpu().numpy().astype(bool)
+            cache = n * H * W * 4 <= self.RAW_CACHE_BUDGET_BYTES
+            raws = np.zeros((n, H, W), np.float32) if cache else None
+            streamer = RawDepthStreamer(lambda i: self.depth_map_path(side, rows[i][0]), n, H, W, chunk_frames=64, device=dev)
+            for f0, f1, raw_dev, present in streamer:
+                _, valid = depth_prepare(raw_dev, nears[f0:f1], fars[f0:f1])
+                keep[f0:f1] = valid.cpu().numpy().astype(bool) & present
+                if cache:
+                    raws[f0:f1] = streamer.host_view
         sel = [rows[i] for i in range(n) if keep[i]]
-        self._raw_cache[side] = (np.array([s[0] for s in sel], dtype=np.int64),
-                                 raws[keep] if raws is not None else np.zeros((0, 0, 0), np.float32))
+        if raws is not None:
+            self._raw_cache[side] = (np.array([s[0] for s in sel], dtype=np.int64), raws[keep])
+        else:
+            self._raw_cache.pop(side, None)
         cols = {k: [] for k in ("ts", "w", "h", "near", "far", "fx", "fy", "cx", "cy", "pos", "rot")}
         for ts, w, h, r in sel:
             fx, fy, cx, cy = depth_camera_params(float(r["fov_left_angle_tangent"]), float(r["fov_right_angle_tangent"]),

@@ -126,6 +126,15 @@ class CameraDataset:
     def __len__(self) -> int:
         return len(self.timestamps)
 
+    def find_nearest_index(self, timestamp: int) -> int:
+        """Index of the frame closest in time (models/camera_dataset.py:79-90; ties go to the earlier frame)."""
+        i = int(np.searchsorted(self.timestamps, timestamp, side="left"))
+        if i == len(self.timestamps):
+            return i - 1
+        if i == 0:
+            return 0
+        return i if abs(self.timestamps[i] - timestamp) < abs(self.timestamps[i - 1] - timestamp) else i - 1
+
     def get_intrinsic_matrices(self) -> np.ndarray:
         """(N,3,3) float32 (camera_dataset.py:93-104)."""
         k = np.zeros((len(self.fx), 3, 3), dtype=np.float32)

@@ -31,16 +31,17 @@ def _torch_device(device) -> torch.device:
     return torch.device("cuda", _device_index(device))
 
 
-def _load_confidence_stack(depth_data_io, side, dataset, n, H, W):
-    """(conf float64 [N,H,W], count int32 [N,H,W], has uint8 [N]) from the per-frame npz files; a missing
-    map leaves the frame unfiltered with a warning (o3d_utils.py:137-139)."""
+def _load_confidence_stack(depth_data_io, side, dataset, f0, f1, H, W):
+    """(conf float64 [n,H,W], count int32 [n,H,W], has uint8 [n]) of frames f0..f1 from the per-frame npz files; a
+    missing map leaves the frame unfiltered with a warning (o3d_utils.py:137-139)."""
+    n = f1 - f0
     conf = np.zeros((n, H, W), np.float64)
     count = np.zeros((n, H, W), np.int32)
     has = np.zeros(n, np.uint8)
     for i in range(n):
-        cm = depth_data_io.load_confidence_map(side=side, timestamp=dataset.timestamps[i])
+        cm = depth_data_io.load_confidence_map(side=side, timestamp=dataset.timestamps[f0 + i])
         if cm is None:
-            print(f"[Warning] Confidence map not found for timestamp {dataset.timestamps[i]}")
+            print(f"[Warning] Confidence map not found for timestamp {dataset.timestamps[f0 + i]}")
             continue
         conf[i], count[i], has[i] = cm.confidence_map, cm.valid_count, 1
     return conf, count, has
@@ -74,10 +75,20 @@ def integrate(dataset: DepthDataset, depth_data_io, side: Side, use_confidence_f
               confidence_threshold: float, valid_count_threshold: int, voxel_size: float, block_resolution: int,
               block_count: int, depth_max: float, trunc_voxel_multiplier: float, device, show_progress: bool = False,
               desc: Optional[str] = None, vbg_opt: Optional[VoxelBlockGrid] = None,
-              confidence: Optional[tuple] = None, batch_frames: int = 64) -> VoxelBlockGrid:
+              confidence: Optional[tuple] = None, batch_frames: int = 256, streaming: Optional[bool] = None,
+              colors=None, color_intrinsics=None) -> VoxelBlockGrid:
     """Drop-in for o3d_utils.integrate (:153-238).  `dataset.transforms` must already be in the OPEN3D
     convention (reconstruct_scene.py:48-51).  `confidence` optionally passes device-resident
-    (conf float64 [N,H,W], count int32 [N,H,W]) straight from K4, skipping the npz round trip."""
+    (conf float64 [N,H,W], count int32 [N,H,W]) straight from K4, skipping the npz round trip.
+
+    Ingest: frames that `build_depth_dataset` kept in memory are integrated from there; otherwise
+    (streaming=None and no cache, or streaming=True) the `.raw` files stream through a bounded pinned ring and two
+    device buffers (ingest.RawDepthStreamer) in chunks of `batch_frames` -- file reads, H2D copies and kernels of
+    consecutive chunks overlap, memory does not grow with the capture.  Both routes give the same grid.
+
+    colors / color_intrinsics: Open3D's colour Integrate overload for grids created with the colour attribute
+    (north-star row A3c).  `colors` is uint8 [N,CH,CW,3] (pinned host or CUDA tensor) or a callable (f0, f1) -> such a
+    tensor for frames f0..f1 (so that a long capture's images are staged chunk by chunk); color_intrinsics [N,3,3]."""
     dev = _torch_device(device)
     vbg = vbg_opt if vbg_opt is not None else VoxelBlockGrid(
         attr_names=("tsdf", "weight"), attr_channels=((1), (1)), voxel_size=voxel_size,
@@ -87,25 +98,45 @@ def integrate(dataset: DepthDataset, depth_data_io, side: Side, use_confidence_f
         return vbg
     extrinsic_wc = dataset.transforms.extrinsics_wc
     intrinsics = compute_o3d_intrinsic_matrices(dataset)
-    raw, present = depth_data_io.load_raw_sequence(side, dataset)
-    H, W = raw.shape[1:]
-    conf = count = has = None
-    if use_confidence_filtered_depth:
+    H, W = int(dataset.heights[0]), int(dataset.widths[0])
+    use_color = colors is not None and vbg.has_color
+    if streaming is None:
+        streaming = not depth_data_io.has_raw_cache(side, dataset)
+
+    def chunk_confidence(f0, f1):
+        if not use_confidence_filtered_depth:
+            return None, None, None
         if confidence is not None:
-            conf, count = confidence
-            has = None
-        else:
-            c, k, h = _load_confidence_stack(depth_data_io, side, dataset, n, H, W)
-            conf, count, has = torch.from_numpy(c), torch.from_numpy(k), torch.from_numpy(h)
+            return confidence[0][f0:f1], confidence[1][f0:f1], None
+        c, k, h = _load_confidence_stack(depth_data_io, side, dataset, f0, f1, H, W)
+        return torch.from_numpy(c), torch.from_numpy(k), torch.from_numpy(h)
+
+    def run(raw_dev, present, f0, f1):
+        conf, count, has = chunk_confidence(f0, f1)
+        lin, valid = depth_prepare(raw_dev, dataset.nears[f0:f1], dataset.fars[f0:f1], conf, count, has,
+                                   confidence_threshold, valid_count_threshold)
+        if not present.all():   # missing files: load_depth_map returns None -> frame skipped (:200-201)
+            valid = valid * torch.from_numpy(present.astype(np.int32)).to(dev)
+        vbg.integrate_sequence(lin, intrinsics[f0:f1], extrinsic_wc[f0:f1], float(depth_max), float(trunc_voxel_multiplier),
+                               1.0, frame_valid=valid, batch_frames=batch_frames,
+                               colors=(colors(f0, f1) if callable(colors) else colors[f0:f1]) if use_color else None,
+                               color_intrinsics=np.asarray(color_intrinsics)[f0:f1] if use_color else None)
+
+    if streaming:
+        from .ingest import stream_side
+        with torch.cuda.device(dev):
+            for f0, f1, raw_dev, present in stream_side(depth_data_io, side, dataset, chunk_frames=batch_frames, device=dev):
+                run(raw_dev, present, f0, f1)
+        return vbg
+    raw, present = depth_data_io.load_raw_sequence(side, dataset)
     raw_t = torch.from_numpy(raw)
     if torch.cuda.is_available():
         raw_t = raw_t.pin_memory()
-    lin, valid = depth_prepare(raw_t.to(dev, non_blocking=True), dataset.nears, dataset.fars, conf, count, has,
-                               confidence_threshold, valid_count_threshold)
-    if not present.all():   # missing files: load_depth_map returns None -> frame skipped (:200-201)
-        valid = valid * torch.from_numpy(present.astype(np.int32)).to(dev)
-    vbg.integrate_sequence(lin, intrinsics, extrinsic_wc, float(depth_max), float(trunc_voxel_multiplier), 1.0,
-                           frame_valid=valid, batch_frames=batch_frames)
+    # confidence maps (and colour frames) are staged per chunk: host memory stays bounded
+    chunk = batch_frames if use_color else max(batch_frames, 1024)
+    for f0 in range(0, n, chunk):
+        f1 = min(n, f0 + chunk)
+        run(raw_t[f0:f1].to(dev, non_blocking=True), present[f0:f1], f0, f1)
     return vbg
 
 

@@ -168,3 +168,92 @@ def test_integrate_frames_host_pipeline_matches_direct(cuda_device, oracle):
         assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x, y.view(np.uint32) if y.dtype == np.float32 else y)
     v, nrm, t = extract_mesh_to_host(a, 1.5)
     assert v.dtype == np.float32 and t.dtype == np.int32 and len(t) > 100
+
+
+def test_streaming_ingest_equals_cached_ingest(cuda_device, oracle, tmp_path):
+    """integrate() fed by the bounded pinned ring (ingest.RawDepthStreamer: file reads -> pinned slots
+    -> two device buffers, chunk by chunk) builds the grid that the whole-side buffer builds, bit for bit, with a
+    missing and a corrupt file in the sequence; build_depth_dataset validates through the same ring."""
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    from mq3d_b200.dataio import DataIO
+    from mq3d_b200.ingest import stream_side
+    from mq3d_b200.models import CoordinateSystem, Side
+    from mq3d_b200.ops import integrate
+    caps = synth.write_project(tmp_path, 23, sides=(Side.LEFT,), width=W, height=H)
+    ts = caps[Side.LEFT].dataset.timestamps
+    np.ones((H, W), "<f4").tofile(tmp_path / "left_depth" / f"{int(ts[5])}.raw")     # invalid: dropped by the dataset build
+    io = DataIO(tmp_path)
+    ds = io.depth.load_depth_dataset(Side.LEFT, use_cache=False)
+    assert len(ds) == 22 and io.depth.has_raw_cache(Side.LEFT, ds)
+    (tmp_path / "left_depth" / f"{int(ts[9])}.raw").unlink()                            # vanishes after the build
+    ds.transforms = ds.transforms.convert_coordinate_system(CoordinateSystem.OPEN3D, is_camera=True)
+    kw = dict(dataset=ds, depth_data_io=io.depth, side=Side.LEFT, use_confidence_filtered_depth=False,
+              confidence_threshold=0.0, valid_count_threshold=0, voxel_size=0.03, block_resolution=16, block_count=64,
+              depth_max=4.0, trunc_voxel_multiplier=10.0, device="CUDA:0")
+    io.depth._raw_cache.clear()
+    a = integrate(**kw, batch_frames=4, streaming=True)            # 6 chunks through a 3-slot ring
+    b = integrate(**kw, batch_frames=4, streaming=False)           # whole side in one pinned buffer
+    ka, ta, wa = sort_blocks(*[x.cpu().numpy() for x in a.export_blocks()[:3]])
+    kb, tb, wb = sort_blocks(*[x.cpu().numpy() for x in b.export_blocks()[:3]])
+    assert len(ka) > 50 and np.array_equal(ka, kb) and np.array_equal(wa, wb)
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    assert wa.max() == 21                                           # 22 dataset frames, one file missing
+    s = stream_side(io.depth, Side.LEFT, ds, chunk_frames=4, device=cuda_device)
+    assert s.host_bytes == 3 * 4 * H * W * 4
+    n = sum(f1 - f0 for f0, f1, _, _ in s)
+    assert n == 22 and s.max_slots_in_use <= 3
+
+
+def test_reconstruct_scene_with_colour(cuda_device, oracle, tmp_path):
+    """depth_integration.integrate_color (extension key): the stage driver builds a coloured grid -- every depth frame
+    takes the colour frame of the same eye nearest in time -- and writes color_mesh.ply; grid and vertex colours equal
+    the oracle's colour branch."""
+    import cv2
+    import mq3d_b200  # noqa: F401
+    from mq3d_b200 import synth
+    from mq3d_b200.config import ReconstructionConfig
+    from mq3d_b200.dataio import DataIO
+    from mq3d_b200.io_utils import read_ply
+    from mq3d_b200.models import CoordinateSystem, Side
+    from mq3d_b200.reconstruct import reconstruct_scene
+    from mq3d_b200.vbg import VoxelBlockGrid
+    n, cw, ch, f = 8, 160, 120, 110.0
+    caps = synth.write_project(tmp_path, n, sides=(Side.LEFT,), width=W, height=H)
+    (tmp_path / "right_depth_descriptors.csv").write_text((tmp_path / "left_depth_descriptors.csv").read_text().splitlines()[0] + "\\n")
+    (tmp_path / "right_depth").mkdir()
+    io = DataIO(tmp_path)
+    cap = caps[Side.LEFT]
+    K, Ewc, Ecw = pipeline_cameras(cap.dataset)
+    cds = synth.make_color_dataset(n, Side.LEFT)
+    cds.widths[:], cds.heights[:] = cw, ch
+    cds.fx[:], cds.fy[:], cds.cx[:], cds.cy[:] = int(f), int(f), cw // 2, ch // 2
+    cds.timestamps[:] = cap.dataset.timestamps + 3                  # 3 ms later than the depth frames: nearest wins
+    io.color.save_color_dataset(Side.LEFT, cds)
+    (tmp_path / "left_camera_rgb").mkdir()
+    cols = [synth.make_color_frame(Ecw[i], width=cw, height=ch, f=f) for i in range(n)]
+    for i in range(n):
+        cv2.imwrite(str(tmp_path / "left_camera_rgb" / f"{int(cds.timestamps[i])}.png"), cv2.cvtColor(cols[i], cv2.COLOR_RGB2BGR))
+    cfg = ReconstructionConfig.parse({
+        "device": "CUDA:0", "use_dataset_cache": False, "estimate_depth_confidences": False, "optimize_depth_pose": False,
+        "optimize_color_pose": False, "use_colorless_vbg_cache": False, "render_color_aligned_depth": False,
+        "depth_integration": {"use_confidence_filtered_depth": False, "voxel_size": 0.03, "block_count": 500, "depth_max": 4.0,
+                              "trunc_voxel_multiplier": 10.0, "integrate_color": True, "batch_frames": 3},
+        "color_optimization": {"weight_threshold": 1.5, "min_triangle_count": 1}})
+    report = reconstruct_scene(io, cfg)
+    assert report["mesh_colored"][0] > 500
+    og = oracle.Grid(0.03, with_color=True)
+    Kc = np.array([[int(f), 0, cw // 2], [0, int(f), ch // 2], [0, 0, 1.0]])
+    ds = cap.dataset
+    for i in range(n):
+        d = oracle.depth_to_linear(cap.raw[i], ds.nears[i], ds.fars[i])
+        og.integrate(og.touch(d, K[i], Ewc[i], 4.0, 10.0), d, K[i], Ewc[i], 4.0, 10.0, color=cols[i], Kc=Kc)
+    g = VoxelBlockGrid.load(str(tmp_path / "reconstruction" / "colorless_vbg.npz"), device=cuda_device)
+    assert g.has_color
+    ok, ot, ow, oc = og.export()
+    a = sort_blocks(ok, ot, ow, oc)
+    b = sort_blocks(*[x.cpu().numpy() for x in g.export_blocks()])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[3].view(np.uint32), b[3].reshape(a[3].shape).view(np.uint32))
+    v, _ = read_ply(tmp_path / "reconstruction" / "color_mesh.ply")
+    assert "red" in v.dtype.names and len(v) == report["mesh_colored"][0] and v["red"].max() > 100

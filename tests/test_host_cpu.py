@@ -262,3 +262,32 @@ def test_integrate_fragment_point_cloud_contract(monkeypatch, capsys):
     assert ops.integrate_fragment_point_cloud("io", ds, Side.LEFT, cfg) is None
     out = capsys.readouterr().out
     assert "integrate_fragment_point_cloud failed for LEFT" in out and "10 - 30" in out
+
+
+def test_raw_depth_streamer_ring(tmp_path):
+    """ingest.RawDepthStreamer, host-only mode: ordered chunks, bounded number of ring slots in use,
+    missing files flagged and zero-filled, truncated files raise in the consumer."""
+    from mq3d_b200.ingest import RawDepthStreamer
+    H, W, n = 6, 8, 37
+    rng = np.random.default_rng(0)
+    frames = rng.random((n, H, W)).astype("<f4")
+    for i in range(n):
+        if i != 11:
+            frames[i].tofile(tmp_path / f"{i}.raw")
+    s = RawDepthStreamer(lambda i: tmp_path / f"{i}.raw", n, H, W, chunk_frames=5, slots=2, device=None, workers=3)
+    assert s.n_chunks == 8 and s.host_bytes == 2 * 5 * H * W * 4
+    seen = 0
+    for f0, f1, chunk, present in s:
+        assert f0 == seen and f1 == min(n, f0 + 5) and chunk.shape == (f1 - f0, H, W)
+        for i in range(f0, f1):
+            if i == 11:
+                assert not present[i - f0] and not chunk[i - f0].any()
+            else:
+                assert present[i - f0] and np.array_equal(chunk[i - f0], frames[i])
+        seen = f1
+    assert seen == n and 1 <= s.max_slots_in_use <= 2
+    (tmp_path / "20.raw").write_bytes((tmp_path / "20.raw").read_bytes()[:40])
+    with pytest.raises(RuntimeError, match="expected 48 float32"):
+        for _ in RawDepthStreamer(lambda i: tmp_path / f"{i}.raw", n, H, W, chunk_frames=5, slots=3, device=None):
+            pass
+    assert list(RawDepthStreamer(lambda i: tmp_path / "x.raw", 0, H, W, device=None)) == []
