@@ -95,7 +95,9 @@ int mq3d_grid_ghost_counts(mq3d_grid *g, int64_t *counts_out, void *stream);
  * the host all-gathers the descriptors (stream-ordered after integration, so the collective is also the
  * "all ranks finished integrating" barrier) and calls mq3d_grid_ghost_pull with the [world] array: one
  * kernel lists the peers' owned blocks inside this rank's shell straight from the peers' key arrays,
- * another copies tsdf | weight | colour from the owners' pools into the local pool.  The caller must
+ * another copies tsdf | weight | colour from the owners' pools into the local pool -- all enqueued without a host
+ * round trip (list length and activation stay on the device; the pool is reserved for the upper bound first).
+ * n_pulled may be NULL; if given the call synchronises to read the number of blocks fetched.  The caller must
  * fence (any stream-ordered collective) before any rank changes its grid again.  Pools exported this
  * way are retired instead of freed on growth, until the grid is destroyed.  Grids living in the same
  * process (rank-by-rank emulation) are read through their plain device pointers. */

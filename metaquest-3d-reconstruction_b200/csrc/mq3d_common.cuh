@@ -271,5 +271,6 @@ int mq3d_grid_fresh_count(mq3d_grid *g, cudaStream_t st);                // same
 int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool *rehashed);
 int mq3d_set_device(int device);
 // Activate + Find for an explicit key list; block indices land in g->idx_scratch.
-int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st);
+int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st,
+                       const int *n_dev = nullptr);
 void mq3d_peer_state_free(mq3d_grid *g);   // mq3d_peer.cu

@@ -530,10 +530,10 @@ extern "C" int mq3d_grid_export(mq3d_grid *g, int32_t *keys_dev, float *tsdf_dev
 // ------------------------------------------------------------------------------------------------
 // integrating = true : keys of a frame about to be integrated -> blocks this rank integrates
 // integrating = false: import (VoxelBlockGrid.load, ghost exchange)  -> any block this rank keeps
-__global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int *n_blocks, int32_t *block_keys,
-                                int64_t capacity, Partition part, bool integrating, int *bad_key_flag) {
+__global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, const int *__restrict__ n_dev, int *n_blocks,
+                                int32_t *block_keys, int64_t capacity, Partition part, bool integrating, int *bad_key_flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
     if (!mq3d_key_in_range(x, y, z)) {
         *bad_key_flag = 1;
@@ -557,10 +557,10 @@ __global__ void k_activate_keys(HashView h, const int32_t *keys, int64_t n, int 
     }
 }
 
-__global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, Partition part, bool integrating,
-                            int32_t *idx_out) {
+__global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, const int *__restrict__ n_dev, Partition part,
+                            bool integrating, int32_t *idx_out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int x = keys[3 * i], y = keys[3 * i + 1], z = keys[3 * i + 2];
     int32_t r = -1;
     if (mq3d_key_in_range(x, y, z) && (!integrating || MQ3D_INTEGRATES(x, y, z, part))) {
@@ -570,8 +570,9 @@ __global__ void k_find_keys(HashView h, const int32_t *keys, int64_t n, Partitio
     idx_out[i] = r;
 }
 
-// Activate + Find (Open3D Integrate preamble).  Leaves block indices in g->idx_scratch.
-int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st) {
+// Activate + Find (Open3D Integrate preamble).  Leaves block indices in g->idx_scratch.  n_dev (optional): the
+// number of keys lives on the device (at most n); nothing is read back.
+int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool integrating, cudaStream_t st, const int *n_dev) {
     if (n > g->idx_scratch_size) {
         cudaFree(g->idx_scratch);
         g->idx_scratch = nullptr;
@@ -580,14 +581,14 @@ int mq3d_grid_activate(mq3d_grid *g, const int32_t *keys_dev, int64_t n, bool in
         g->idx_scratch_size = sz;
     }
     // worst case every key is new: make room first so indices never exceed the pool
-    MQ3D_TRY(mq3d_grid_sync_count(g, st));
+    MQ3D_TRY(mq3d_grid_fresh_count(g, st));
     bool rehashed;
     MQ3D_TRY(mq3d_grid_ensure_capacity(g, g->n_blocks_host + n, st, &rehashed));
     MQ3D_CUDA(cudaMemsetAsync(g->counter_dev, 0, sizeof(int), st));
     unsigned grid = (unsigned)((n + 255) / 256);
-    k_activate_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->n_blocks_dev, g->block_keys, g->capacity,
+    k_activate_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, n_dev, g->n_blocks_dev, g->block_keys, g->capacity,
                                           g->part, integrating, g->counter_dev);
-    k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, g->part, integrating, g->idx_scratch);
+    k_find_keys<<<grid, 256, 0, st>>>(g->hash, keys_dev, n, n_dev, g->part, integrating, g->idx_scratch);
     MQ3D_CUDA(cudaGetLastError());
     g->count_dirty = 1;
     g->mc_state = 0;

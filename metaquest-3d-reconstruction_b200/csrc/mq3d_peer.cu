@@ -79,7 +79,7 @@ extern "C" int mq3d_grid_peer_descriptor(mq3d_grid *g, void *desc_out, void *str
     MQ3D_REQUIRE(g->part.world <= MQ3D_MAX_PEERS, "peer ghost pull supports at most 64 ranks");
     MQ3D_TRY(mq3d_set_device(g->device));
     MQ3D_TRY(peer_state(g));
-    MQ3D_TRY(mq3d_grid_sync_count(g, as_stream(stream)));
+    MQ3D_TRY(mq3d_grid_fresh_count(g, as_stream(stream)));     // no synchronisation right after a sequence call
     mq3d_peer_state *p = g->peer;
     PeerDesc d;
     memset(&d, 0, sizeof(d));
@@ -129,8 +129,9 @@ __global__ void k_ghost_scan(const PeerView *__restrict__ peers, Partition part,
 // local pool; all loads of a phase are issued before the first store (NVLink latency)
 __global__ void __launch_bounds__(256)
 k_ghost_copy(const PeerView *__restrict__ peers, const int2 *__restrict__ pull_src, const int32_t *__restrict__ idx,
-             float *__restrict__ tsdf, float *__restrict__ weight, float *__restrict__ color) {
+             const int *__restrict__ count, float *__restrict__ tsdf, float *__restrict__ weight, float *__restrict__ color) {
     const int64_t i = blockIdx.x;
+    if (i >= *count) return;           // the grid covers the upper bound; the list length lives on the device
     const int b = idx[i];
     if (b < 0) return;
     const int2 s = pull_src[i];
@@ -197,8 +198,8 @@ static int resolve_peer_ptr(mq3d_grid *g, const PeerDesc &d, int a, void **out) 
 }
 
 extern "C" int mq3d_grid_ghost_pull(mq3d_grid *g, const void *descs, int64_t *n_pulled, void *stream) {
-    MQ3D_REQUIRE(g && descs && n_pulled, "null argument");
-    *n_pulled = 0;
+    MQ3D_REQUIRE(g && descs, "null argument");
+    if (n_pulled) *n_pulled = 0;
     const int world = g->part.world, rank = g->part.rank;
     if (world <= 1) return MQ3D_OK;
     MQ3D_REQUIRE(world <= MQ3D_MAX_PEERS, "peer ghost pull supports at most 64 ranks");
@@ -244,13 +245,16 @@ extern "C" int mq3d_grid_ghost_pull(mq3d_grid *g, const void *descs, int64_t *n_
     dim3 grid((unsigned)((most + 255) / 256), (unsigned)world);
     k_ghost_scan<<<grid, 256, 0, st>>>(p->views_dev, g->part, g->counter_dev + 5, p->pull_keys, p->pull_src);
     MQ3D_CUDA(cudaGetLastError());
-    MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host + 5, g->counter_dev + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
-    MQ3D_CUDA(cudaStreamSynchronize(st));
-    const int64_t m = g->pinned_host[5];
-    if (m == 0) return MQ3D_OK;
-    MQ3D_TRY(mq3d_grid_activate(g, p->pull_keys, m, /*integrating=*/false, st));
-    k_ghost_copy<<<(unsigned)m, 256, 0, st>>>(p->views_dev, p->pull_src, g->idx_scratch, g->tsdf, g->weight, g->color);
+    // Everything below is sized by the upper bound `total` (all blocks of all peers) and reads the list length on the
+    // device: no host round trip between the scan and the copy.  The pool is reserved for the bound up front.
+    MQ3D_TRY(mq3d_grid_activate(g, p->pull_keys, total, /*integrating=*/false, st, g->counter_dev + 5));
+    k_ghost_copy<<<(unsigned)total, 256, 0, st>>>(p->views_dev, p->pull_src, g->idx_scratch, g->counter_dev + 5, g->tsdf, g->weight,
+                                                  g->color);
     MQ3D_CUDA(cudaGetLastError());
-    *n_pulled = m;
+    if (n_pulled) {                     // optional: the caller wants the count (synchronises)
+        MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host + 5, g->counter_dev + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MQ3D_CUDA(cudaStreamSynchronize(st));
+        *n_pulled = g->pinned_host[5];
+    }
     return MQ3D_OK;
 }

@@ -169,41 +169,54 @@ def exchange_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None
     return total
 
 
-def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fence: bool = True) -> int:
+def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fence: bool = True,
+                count: bool = True) -> int:
     """Owned-only integration mode, peer-memory variant of exchange_ghosts: all-gather the 512-byte pool
-    descriptors (CUDA IPC handles; the collective is stream-ordered after integration, so it is also the
-    "everyone has finished integrating" barrier), then each rank copies the blocks of its ghost shell straight
-    out of the owners' pools over NVLink (vbg.ghost_pull: two kernels, no staging, no send/recv, no import).
-    A tiny all-reduce afterwards keeps any rank's later work (grid reset, next integration) from overtaking
-    a peer that is still reading its pool and carries the per-rank status; with fence=True (default) the
-    host reads it, so a failure anywhere raises PeerPullError everywhere (the grids are still valid for
-    exchange_ghosts).  Returns the number of ghost blocks fetched."""
+    descriptors (CUDA IPC handles + block counts; the collective is stream-ordered after integration, so it is also
+    the "everyone has finished integrating" barrier), then each rank copies the blocks of its ghost shell straight
+    out of the owners' pools over NVLink (vbg.ghost_pull: scan, activation and copy kernels enqueued back to back,
+    no staging, no send/recv, no import).  A one-word all-reduce afterwards keeps any rank's later work (grid reset,
+    next integration) from overtaking a peer that is still reading its pool.
+
+    Host synchronisation: one, to read the gathered descriptors.  The all-reduce also carries a status word, read on
+    the host only while the set of exported pools is new to this process (first pull, or some pool was re-allocated
+    -- every rank sees the same table, so all ranks agree on that): mapping a peer's pool is the step that can fail,
+    and then every rank raises PeerPullError together (the grids are still valid for exchange_ghosts).  A rank that
+    cannot export its own pool publishes an empty descriptor, which all ranks see at once.  count=False skips the
+    read-back of the number of blocks fetched (returns -1).  fence=False never reads the status."""
     import torch.distributed as dist
     if rank is None:
         rank, world = dist.get_rank(), dist.get_world_size()
     if world == 1:
         return 0
     dev = torch.device(vbg.device)
-    ok, err, n = 1, None, 0
+    err, n = None, -1
     try:
         mine = torch.from_numpy(vbg.peer_descriptor()).to(dev, non_blocking=True)
     except Exception as e:                      # e.g. CUDA IPC not permitted in this container
-        ok, err = 0, e
+        err = e
         mine = torch.zeros(PEER_DESC_BYTES, dtype=torch.uint8, device=dev)
     table = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)     # flat: valid for NCCL and gloo
     dist.all_gather_into_tensor(table, mine)
-    if ok:
-        try:
-            n = vbg.ghost_pull(table.cpu().numpy().reshape(world, mine.numel()))
-        except Exception as e:
-            ok, err = 0, e
+    descs = table.cpu().numpy().reshape(world, mine.numel())
+    if not descs[:, :4].any(axis=1).all():      # some rank could not export (magic == 0): nobody pulls
+        raise PeerPullError(f"peer-memory ghost pull unavailable on some rank (this rank: {err})")
+    # identity of the exported pools: everything but the per-step block count (bytes 32..40)
+    ident = descs[:, :32].tobytes() + descs[:, 40:336].tobytes()
+    known = getattr(vbg, "_peer_pools_seen", None) == ident
+    ok = 1
+    try:
+        n = vbg.ghost_pull(descs, want_count=count)
+    except Exception as e:
+        ok, err = 0, e
     # the fence doubles as the status exchange: every rank learns whether every pull was issued
     tok = _fence_token(dev)
     tok.fill_(ok)
     dist.all_reduce(tok, op=dist.ReduceOp.MIN)
-    if fence or not ok:
+    if not ok or (fence and not known):
         if int(tok.item()) == 0:
             raise PeerPullError(f"peer-memory ghost pull failed on some rank (this rank: {err})")
+        vbg._peer_pools_seen = ident
     return n
 
 
@@ -222,7 +235,7 @@ def fill_ghost_shell(vbg, rank: Optional[int] = None, world: Optional[int] = Non
     the mode that was used."""
     if mode == "pull" and _PULL_USABLE[0]:
         try:
-            pull_ghosts(vbg, rank, world)
+            pull_ghosts(vbg, rank, world, count=False)
             return "pull"
         except PeerPullError:
             _PULL_USABLE[0] = False

@@ -192,17 +192,19 @@ class VoxelBlockGrid:
             _lib.check(_lib.lib().mq3d_grid_peer_descriptor(self._h, desc.ctypes.data_as(C.c_void_p), _stream()))
         return desc
 
-    def ghost_pull(self, descs: np.ndarray) -> int:
+    def ghost_pull(self, descs: np.ndarray, want_count: bool = True) -> int:
         """Fetch the ghost shell straight from the owners' pools (peer memory over NVLink).  descs: uint8
-        [world, 512], row r = rank r's peer_descriptor().  Asynchronous on the current stream apart from one
-        count readback; the caller fences (stream-ordered collective) before any grid changes again."""
+        [world, 512], row r = rank r's peer_descriptor().  Everything is enqueued on the current stream without a
+        host round trip; want_count=True additionally reads back the number of blocks fetched (synchronises),
+        otherwise -1 is returned.  The caller fences (stream-ordered collective) before any grid changes again."""
         descs = np.ascontiguousarray(descs, np.uint8)
         world = self.partition[1] if self.partition else 1
         if descs.shape != (world, PEER_DESC_BYTES):
             raise RuntimeError(f"descs must be uint8 [{world}, {PEER_DESC_BYTES}]")
-        n = C.c_int64()
+        n = C.c_int64(-1)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().mq3d_grid_ghost_pull(self._h, descs.ctypes.data_as(C.c_void_p), C.byref(n), _stream()))
+            _lib.check(_lib.lib().mq3d_grid_ghost_pull(self._h, descs.ctypes.data_as(C.c_void_p),
+                                                       C.byref(n) if want_count else None, _stream()))
         return int(n.value)
 
     def ghost_select_packed(self, dest_rank: int, count: Optional[int] = None):

@@ -220,7 +220,7 @@ def test_reconstruct_scene_with_colour(cuda_device, oracle, tmp_path):
     from mq3d_b200.vbg import VoxelBlockGrid
     n, cw, ch, f = 8, 160, 120, 110.0
     caps = synth.write_project(tmp_path, n, sides=(Side.LEFT,), width=W, height=H)
-    (tmp_path / "right_depth_descriptors.csv").write_text((tmp_path / "left_depth_descriptors.csv").read_text().splitlines()[0] + "\\n")
+    (tmp_path / "right_depth_descriptors.csv").write_text((tmp_path / "left_depth_descriptors.csv").read_text().splitlines()[0] + "\n")
     (tmp_path / "right_depth").mkdir()
     io = DataIO(tmp_path)
     cap = caps[Side.LEFT]
