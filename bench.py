@@ -301,31 +301,49 @@ def run_gpu(args):
     # ---- multi-GPU parity: the partitioned grids, summed, are the single-GPU grid ---------------------
     parity = None
     if sharded:
+        from mq3d_b200.dist import gather_mesh
         st0, mesh0, _ = step_device()
         nb, cs = block_checksum(vbg, owned_by=(rank, world, args.tile))
         red = torch.tensor([nb, cs, int(mesh0[2].shape[0])], dtype=torch.int64, device=device)
         dist.all_reduce(red)
+        whole = gather_mesh(mesh0[0], mesh0[1], mesh0[2], dst=0)          # the concatenated per-rank meshes on rank 0
         del mesh0
         if rank == 0:
+            from mq3d_b200.geometry import TriangleMesh
+            from mq3d_b200.meshfilter import filter_mesh_components_device
             ref = VoxelBlockGrid(attr_names=attrs, voxel_size=cfg["voxel"], block_count=cfg["block_count"], device=device)
             lin, valid = depth_prepare(wl["raw"], wl["nears"], wl["fars"])
             ref.integrate_sequence(lin, wl["K"], wl["Ewc"], cfg["depth_max"], cfg["trunc"], 1.0, frame_valid=valid,
                                    colors=wl["colors"], color_intrinsics=wl["Kc"], batch_frames=args.batch)
             del lin
             nb1, cs1 = block_checksum(ref)
-            t1 = int(ref.extract_triangle_mesh_arrays(cfg["weight_thr"])[2].shape[0])
+            m1 = ref.extract_triangle_mesh_arrays(cfg["weight_thr"])
+            v1, t1 = int(m1[0].shape[0]), int(m1[2].shape[0])
+            # vertices on ghost edges are emitted by every rank that references them: the device mesh filter's weld
+            # (identical coordinates -> first occurrence) turns the concatenation into the single-GPU vertex set
+            welded, _ = filter_mesh_components_device(TriangleMesh(whole[0], whole[2], whole[1]), 1)
+            vw, tw = int(welded.vertex.positions.shape[0]), int(welded.triangle.indices.shape[0])
+            # (the single-grid mesh goes through the same weld: a zero crossing exactly on a voxel corner yields the same
+            # position on up to three lattice edges)
+            single, _ = filter_mesh_components_device(TriangleMesh(m1[0], m1[2], m1[1]), 1)
+            v1w = int(single.vertex.positions.shape[0])
             ref.close()
-            del ref
-            torch.cuda.empty_cache()
+            del ref, m1, welded, single
             parity = {"blocks_single": nb1, "blocks_sharded": int(red[0]), "checksum_single": cs1,
                       "checksum_sharded": int(red[1]) % _P, "triangles_single": t1, "triangles_sharded": int(red[2]),
+                      "vertices_single": v1, "vertices_single_welded": v1w, "vertices_gathered": int(whole[0].shape[0]),
+                      "vertices_welded": vw,
+                      "triangles_welded": tw,
                       "what": "tsdf + weight bit patterns of every owned block (position- and key-weighted sum "
-                              "mod 2^31-1) summed over ranks vs one unpartitioned grid on rank 0"}
+                              "mod 2^31-1) summed over ranks vs one unpartitioned grid on rank 0; gathered mesh "
+                              "welded by the device mesh filter vs the single-grid mesh"}
             parity["equal"] = (parity["blocks_single"] == parity["blocks_sharded"]
                                and parity["checksum_single"] == parity["checksum_sharded"]
-                               and parity["triangles_single"] == parity["triangles_sharded"])
+                               and parity["triangles_single"] == parity["triangles_sharded"] == tw and v1w == vw)
             if not parity["equal"]:
                 raise SystemExit(f"multi-GPU parity check failed: {parity}")
+        del whole
+        torch.cuda.empty_cache()
 
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -376,13 +394,16 @@ def run_gpu(args):
             return (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
         return to_host((got[0], got[1], got[2]) + ((got[4],) if color else ()))
 
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
+    host_mesh = None
+    for _ in range(min(args.warmup, 3)):
+        host_mesh = None      # the previous step's mesh is released first, as in the device-resident loop: the pinned
+        host_mesh = step_e2e()    # staging of the read-back is then reused instead of being allocated a second time
     barrier()
     e2e_steps = max(1, min(args.steps, 5))
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
+        host_mesh = None
         host_mesh = step_e2e()
     f1.record()
     barrier()

@@ -266,6 +266,34 @@ struct mq3d_grid {
     int64_t mc_V, mc_T;
 };
 
+#include <stdlib.h>
+// MQ3D_TRACE: device time of the phases of a call (CUDA events on the stream), printed to stderr
+struct MqTrace {
+    cudaStream_t st;
+    bool on;
+    int n;
+    cudaEvent_t ev[8];
+    const char *name[8];
+    explicit MqTrace(cudaStream_t s) : st(s), on(getenv("MQ3D_TRACE") != nullptr), n(0) { mark("start"); }
+    void mark(const char *what) {
+        if (!on || n >= 8) return;
+        if (cudaEventCreate(&ev[n]) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(ev[n], st);
+        name[n++] = what;
+    }
+    void report(const char *call) {     // after a stream synchronisation
+        if (!on) return;
+        fprintf(stderr, "[mq3d] %s:", call);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s %.3f ms", name[i], ms);
+        }
+        fprintf(stderr, "\n");
+    }
+    ~MqTrace() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
+};
+
 int mq3d_grid_sync_count(mq3d_grid *g, cudaStream_t st);                 // refresh n_blocks_host (synchronises)
 int mq3d_grid_fresh_count(mq3d_grid *g, cudaStream_t st);                // same, but only if blocks may have been added since
 int mq3d_grid_ensure_capacity(mq3d_grid *g, int64_t need, cudaStream_t st, bool *rehashed);

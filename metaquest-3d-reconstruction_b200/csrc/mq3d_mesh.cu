@@ -723,33 +723,6 @@ static int mc_prepare(mq3d_grid *g, cudaStream_t st) {
     return MQ3D_OK;
 }
 
-// MQ3D_TRACE: device time of the phases of a call (CUDA events on the stream), printed to stderr
-struct MqTrace {
-    cudaStream_t st;
-    bool on;
-    int n;
-    cudaEvent_t ev[8];
-    const char *name[8];
-    explicit MqTrace(cudaStream_t s) : st(s), on(getenv("MQ3D_TRACE") != nullptr), n(0) { mark("start"); }
-    void mark(const char *what) {
-        if (!on || n >= 8) return;
-        if (cudaEventCreate(&ev[n]) != cudaSuccess) { on = false; return; }
-        cudaEventRecord(ev[n], st);
-        name[n++] = what;
-    }
-    void report(const char *call) {     // after a stream synchronisation
-        if (!on) return;
-        fprintf(stderr, "[mq3d] %s:", call);
-        for (int i = 1; i < n; ++i) {
-            float ms = 0.0f;
-            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            fprintf(stderr, " %s %.3f ms", name[i], ms);
-        }
-        fprintf(stderr, "\n");
-    }
-    ~MqTrace() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
-};
-
 static int mc_classify(mq3d_grid *g, float weight_threshold, cudaStream_t st, MqTrace *tr = nullptr) {
     const int64_t n = g->mc_blocks;
     k_mc_rows<<<(unsigned)n, 256, 0, st>>>(g->tsdf, g->weight, n, weight_threshold, g->mc_rows);

@@ -240,17 +240,25 @@ extern "C" int mq3d_grid_ghost_pull(mq3d_grid *g, const void *descs, int64_t *n_
         MQ3D_CUDA(cudaMalloc(&p->pull_src, sizeof(int2) * cap));
         p->pull_cap = cap;
     }
+    MqTrace tr(st);
     MQ3D_CUDA(cudaMemcpyAsync(p->views_dev, p->views_host, sizeof(PeerView) * world, cudaMemcpyHostToDevice, st));
     MQ3D_CUDA(cudaMemsetAsync(g->counter_dev + 5, 0, sizeof(int), st));
     dim3 grid((unsigned)((most + 255) / 256), (unsigned)world);
     k_ghost_scan<<<grid, 256, 0, st>>>(p->views_dev, g->part, g->counter_dev + 5, p->pull_keys, p->pull_src);
     MQ3D_CUDA(cudaGetLastError());
+    tr.mark("scan");
     // Everything below is sized by the upper bound `total` (all blocks of all peers) and reads the list length on the
     // device: no host round trip between the scan and the copy.  The pool is reserved for the bound up front.
     MQ3D_TRY(mq3d_grid_activate(g, p->pull_keys, total, /*integrating=*/false, st, g->counter_dev + 5));
+    tr.mark("activate");
     k_ghost_copy<<<(unsigned)total, 256, 0, st>>>(p->views_dev, p->pull_src, g->idx_scratch, g->counter_dev + 5, g->tsdf, g->weight,
                                                   g->color);
     MQ3D_CUDA(cudaGetLastError());
+    tr.mark("copy");
+    if (tr.on) {
+        cudaStreamSynchronize(st);
+        tr.report("ghost_pull");
+    }
     if (n_pulled) {                     // optional: the caller wants the count (synchronises)
         MQ3D_CUDA(cudaMemcpyAsync(g->pinned_host + 5, g->counter_dev + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
         MQ3D_CUDA(cudaStreamSynchronize(st));

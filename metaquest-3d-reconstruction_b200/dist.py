@@ -191,6 +191,13 @@ def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fe
         return 0
     dev = torch.device(vbg.device)
     err, n = None, -1
+    import os as _os
+    import time as _time
+    trace = _os.environ.get("MQ3D_TRACE") is not None
+    t_start = _time.perf_counter()
+    if trace:
+        torch.cuda.synchronize()
+        t_start = _time.perf_counter()
     try:
         mine = torch.from_numpy(vbg.peer_descriptor()).to(dev, non_blocking=True)
     except Exception as e:                      # e.g. CUDA IPC not permitted in this container
@@ -199,6 +206,7 @@ def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fe
     table = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)     # flat: valid for NCCL and gloo
     dist.all_gather_into_tensor(table, mine)
     descs = table.cpu().numpy().reshape(world, mine.numel())
+    t_gather = _time.perf_counter()
     if not descs[:, :4].any(axis=1).all():      # some rank could not export (magic == 0): nobody pulls
         raise PeerPullError(f"peer-memory ghost pull unavailable on some rank (this rank: {err})")
     # identity of the exported pools: everything but the per-step block count (bytes 32..40)
@@ -217,6 +225,11 @@ def pull_ghosts(vbg, rank: Optional[int] = None, world: Optional[int] = None, fe
         if int(tok.item()) == 0:
             raise PeerPullError(f"peer-memory ghost pull failed on some rank (this rank: {err})")
         vbg._peer_pools_seen = ident
+    if trace:
+        torch.cuda.synchronize()
+        import sys as _sys
+        print(f"[mq3d r{rank}] pull_ghosts: descriptors+wait {1e3 * (t_gather - t_start):.3f} ms, pull+fence "
+              f"{1e3 * (_time.perf_counter() - t_gather):.3f} ms", file=_sys.stderr)
     return n
 
 
