@@ -402,12 +402,15 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, 5))
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
+    e2e_marks = [f0]
     for _ in range(e2e_steps):
         host_mesh = None
         host_mesh = step_e2e()
+        e2e_marks.append(ev())
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
+    e2e_each = [round(a.elapsed_time(b), 3) for a, b in zip(e2e_marks[:-1], e2e_marks[1:])]
     h2d = raw_host.numel() * 4
     h2d_note = "depth frames by DMA from pinned memory, chunked on a copy stream under K1/K2/K3"
     if color and not sharded:
@@ -492,7 +495,8 @@ def run_gpu(args):
                         "bytes": "8 B x active voxels x (17/16)^3 + 24 B/vertex + 12 B/triangle (SURVEY 8d)",
                         "traffic": profile_figure("mc_traffic", args.workload), "ms": mc_ms},
         "e2e": {"value": frames_job / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "h2d_note": h2d_note},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "ms_each_step_rank0": e2e_each,
+                "h2d_note": h2d_note},
         # per step on each rank: reset fill (1) + K1 prepare/finalize (2) + per batch [colour resample] + touch +
         # sort + integrate x 2 (unguarded / guarded division, one of them returns at once) + bitmap clear + MC
         # neighbours/classify/scan/emit [+ colours]

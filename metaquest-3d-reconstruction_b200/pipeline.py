@@ -137,7 +137,7 @@ _COPY_STREAMS: dict = {}
 def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
     key = (dev.type, dev.index)
     if key not in _COPY_STREAMS:
-        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)    # uploads / resampling get free SM slots first
     return _COPY_STREAMS[key]
 
 
