@@ -174,7 +174,7 @@ def test_integrate_shapes_are_bit_identical(cuda_device, oracle, color, monkeypa
                   color_intrinsics=np.tile(np.array([[f, 0, cw / 2.0], [0, f, ch / 2.0], [0, 0, 1.0]]), (n, 1, 1)))
     attrs = ("tsdf", "weight", "color") if color else ("tsdf", "weight")
     results = {}
-    for variant in ("0", "9", "8", "12", "20", "21", "22", "23", "24", "25", "26"):
+    for variant in ("0", "9", "8", "12", "20", "21", "22", "23", "24", "25", "26", "30", "31", "32", "33", "34", "40"):
         monkeypatch.setenv("MQ3D_INTEG_VARIANT", variant)
         g = VoxelBlockGrid(attr_names=attrs, voxel_size=0.02, block_count=3000, device=cuda_device)
         st = g.integrate_sequence(lin, K, Ewc, 4.0, 10.0, batch_frames=5, **kw)
