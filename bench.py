@@ -570,6 +570,23 @@ def aux_block(device, args):
         row = {"frames": wl["n"], "ms_per_step": ms, "frames_per_s": wl["n"] / (ms * 1e-3),
                "k_integrate_ms": st.integrate_ms, "active_blocks": st.num_blocks,
                "mesh": {"vertices": int(mesh[0].shape[0]), "triangles": int(mesh[2].shape[0])}}
+        if not cfg["color"]:
+            # the per-frame call shape of the level-1 drop-in (o3d_utils.py:212-229: compute_unique_block_coordinates ->
+            # integrate, one frame at a time, synchronous like Open3D's) on the same frames
+            lin, valid = depth_prepare(wl["raw"], wl["nears"], wl["fars"])
+
+            def per_frame():
+                vbg.reset()
+                for i in range(wl["n"]):
+                    keys = vbg.compute_unique_block_coordinates(lin[i], wl["K"][i], wl["Ewc"][i], 1.0, cfg["depth_max"],
+                                                                cfg["trunc"])
+                    vbg.integrate(keys, lin[i], wl["K"][i], wl["Ewc"][i], 1.0, cfg["depth_max"], cfg["trunc"])
+                return vbg.num_blocks()
+            pf_ms, nb_pf = timed(per_frame, steps=2, warmup=1)
+            row["per_frame_api"] = {"ms_per_step": pf_ms, "frames_per_s": wl["n"] / (pf_ms * 1e-3), "active_blocks": int(nb_pf),
+                                    "what": "VoxelBlockGrid.compute_unique_block_coordinates + .integrate per frame "
+                                            "(two synchronous C-ABI calls per frame; HBM / launch bound)"}
+            del lin
         if cfg["color"]:
             # K6 (o3d_utils.py:324-342): filtered mesh -> LBVH -> 1280x960 pinhole rays per colour frame
             tm = filter_mesh_components(TriangleMesh(mesh[0], mesh[2], mesh[1]), min_triangle_count=5000)

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base dem
 echo "launch list rc=$?"
 $CMD > $OUT/r2_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:k_integrate<\(bool\)0, \(bool\)1, \(int\)128, \(int\)6, \(int\)2' -s 7 -c 2 -f -o $OUT/r2_integrate_5mm $CMD > $OUT/r2_ncu_integ.log 2>&1
+    -k 'regex:k_integrate<\(bool\)0, \(bool\)1, \(int\)128, \(int\)8, \(int\)2' -s 7 -c 2 -f -o $OUT/r2_integrate_5mm $CMD > $OUT/r2_ncu_integ.log 2>&1
 echo "integrate rc=$?"
 $CMD > $OUT/r2_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
@@ -20,9 +20,13 @@ echo "others rc=$?"
 CMDC="python bench.py --workload quest300_rgb_v10mm --steps 1 --warmup 1 --no-aux --no-cpu-baseline"
 $CMDC > $OUT/r2_plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:k_integrate<\(bool\)1, \(bool\)1, \(int\)128, \(int\)8, \(int\)2' -s 3 -c 1 -f -o $OUT/r2_integrate_rgb $CMDC > $OUT/r2_ncu_integ_rgb.log 2>&1
+    -k 'regex:k_integrate<\(bool\)1, \(bool\)1, \(int\)128, \(int\)7, \(int\)2' -s 3 -c 1 -f -o $OUT/r2_integrate_rgb $CMDC > $OUT/r2_ncu_integ_rgb.log 2>&1
 echo "integrate rgb rc=$?"
 $CMDC > $OUT/r2_plain5.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k 'regex:^(void )?k_' -c 400 \
     --csv --log-file $OUT/r2_launches_rgb.csv $CMDC > $OUT/r2_ncu_launches_rgb.log 2>&1
 echo "launch list rgb rc=$?"
+$CMD > $OUT/r2_plain6.log 2>&1 &&
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k 'regex:^(void )?(k_mc_|k_scan_)' -s 6 -c 6 -f -o $OUT/r2_mc_5mm $CMD > $OUT/r2_ncu_mc.log 2>&1
+echo "mc rc=$?"
