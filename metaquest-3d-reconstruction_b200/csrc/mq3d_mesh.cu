@@ -137,6 +137,7 @@ k_mc_classify(const uint32_t *__restrict__ rows_vs, const int32_t *__restrict__ 
         // ---- phase A: one thread per (y,z) row of the (-1..16)^2 neighbourhood: the row's 16 interior bits from the
         // block that holds it, the x = -1 / x = 16 bits from that block's -x / +x neighbours (bit i <-> x = i - 1);
         // missing blocks contribute zeros
+        unsigned sign_mix = 0;                 // bit 0: a valid voxel with tsdf < 0, bit 1: a valid voxel with tsdf >= 0
         for (int r = tid; r < SROW_WORDS; r += MC_CLASSIFY_THREADS) {
             const int ry = r % ROW_R - 1, rz = r / ROW_R - 1;
             const int k0 = 3 * nb_of(ry) + 9 * nb_of(rz);
@@ -150,6 +151,7 @@ k_mc_classify(const uint32_t *__restrict__ rows_vs, const int32_t *__restrict__ 
             s_valid[r] = vrow;
             s_sign[r] = srow;
             srow_out[b * SROW_WORDS + r] = srow;
+            sign_mix |= ((srow & vrow) != 0u ? 1u : 0u) | ((~srow & vrow) != 0u ? 2u : 0u);
         }
         if (tid < 4) {
             // cubes count only in owned blocks (multi-GPU partition); cube x = -1 lies in block x - 1, cube y / z = -1 in
@@ -161,7 +163,19 @@ k_mc_classify(const uint32_t *__restrict__ rows_vs, const int32_t *__restrict__ 
             }
             s_own[tid] = own;
         }
-        __syncthreads();
+        // Most blocks of a truncation band hold no surface: a surface cube (and a marked edge) needs eight valid corners
+        // with differing signs, so when the valid voxels of the (-1..16)^3 neighbourhood all have the same sign there is
+        // nothing to emit.  Such a block writes zero counts and none of its tables -- nobody reads them: emit skips the
+        // block, and a neighbour resolves vertex ids only on marked edges, which this neighbourhood does not have.
+        // (__syncthreads_or is a vote, not a bitwise OR: one barrier per bit; the first one replaces the staging barrier)
+        const int any_set = __syncthreads_or((int)(sign_mix & 1u)), any_clear = __syncthreads_or((int)(sign_mix & 2u));
+        if (!(any_set && any_clear)) {
+            if (tid == 0) {
+                counts[2 * b] = 0;
+                counts[2 * b + 1] = 0;
+            }
+            return;
+        }
     // ---- phase C: one thread per own row (y,z): edge marks, surface cubes, triangle count ----
     int cnt[5] = {0, 0, 0, 0, 0};   // popc(x marks), popc(y marks), popc(z marks), triangles, surface cubes
     {
