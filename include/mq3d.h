@@ -166,6 +166,13 @@ int mq3d_integrate_sequence(mq3d_grid *g, const float *depth_dev, const int32_t 
                             const double *E, float depth_scale, float depth_max,
                             float trunc_voxel_multiplier, int batch_frames, mq3d_seq_stats *stats,
                             void *stream);
+/* Batch gates for the NEXT mq3d_integrate_sequence / _rgbx call on this grid: events[i] (a cudaEvent_t, or NULL) is
+ * waited for on the call's stream before batch i is enqueued, so one call can consume frames that another stream
+ * is still producing (host->device upload + mq3d_depth_prepare of chunk i+1 while chunk i integrates) without a
+ * host synchronisation per chunk -- the streaming form of the frame loop in integrate() (o3d_utils.py:231-236),
+ * where load_depth_map of the next frame could overlap the integration of the current one.  The list is copied;
+ * it is consumed (cleared) by that call.  n_events = 0 clears it. */
+int mq3d_grid_set_batch_gates(mq3d_grid *g, const void *const *events, int n_events);
 /* Colour on the depth pixel grid.  The colour branch of Open3D's Integrate reads, for a voxel that projects
  * to depth pixel (ui, vi), the colour pixel round(Project_colourK(Unproject_depthK(ui, vi, 1))) under an
  * identity extrinsic -- a function of the depth pixel alone.  mq3d_color_resample evaluates it once per

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mq3d_last_error", "mq3d_version", "mq3d_selftest_rcp",
     "mq3d_grid_create", "mq3d_grid_destroy", "mq3d_grid_reset", "mq3d_grid_reserve",
     "mq3d_grid_num_blocks", "mq3d_grid_info", "mq3d_grid_pool", "mq3d_grid_export", "mq3d_grid_import",
-    "mq3d_grid_set_partition", "mq3d_grid_set_ghost_mode", "mq3d_grid_ghost_select",
+    "mq3d_grid_set_partition", "mq3d_grid_set_ghost_mode", "mq3d_grid_set_batch_gates", "mq3d_grid_ghost_select",
     "mq3d_grid_ghost_counts", "mq3d_grid_peer_descriptor", "mq3d_grid_ghost_pull",
     "mq3d_depth_prepare", "mq3d_touch", "mq3d_integrate", "mq3d_integrate_sequence",
     "mq3d_color_resample", "mq3d_integrate_sequence_rgbx",
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         "mq3d_grid_import": [vp, vp, vp, vp, vp, i64, vp],
         "mq3d_grid_set_partition": [vp, i32, i32, i32],
         "mq3d_grid_set_ghost_mode": [vp, i32],
+        "mq3d_grid_set_batch_gates": [vp, vp, i32],
         "mq3d_grid_ghost_select": [vp, i32, C.POINTER(i64), vp, vp, vp, vp, vp],
         "mq3d_grid_ghost_counts": [vp, C.POINTER(i64), vp],
         "mq3d_grid_peer_descriptor": [vp, vp, vp],

@@ -251,6 +251,10 @@ struct mq3d_grid {
     unsigned long long *stat_dev;      // [2]
     cudaEvent_t *events;               // persistent timing events of the sequence path
     int n_events;
+    // batch gates of the NEXT sequence call (mq3d_grid_set_batch_gates): cudaEvent_t per batch, waited for on the
+    // stream before that batch is enqueued; host copy, cleared by the call
+    void **gates;
+    int n_gates;
     // marching cubes scratch (valid between *_count and *_fill)
     int32_t *mc_nb;       // [n][27]
     uint32_t *mc_rows;    // [n][256] (validity << 16) | sign of every x-row

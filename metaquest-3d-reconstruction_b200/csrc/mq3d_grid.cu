@@ -234,6 +234,7 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->stat_dev);
     for (int q = 0; q < g->n_events; ++q) cudaEventDestroy(g->events[q]);
     free(g->events);
+    free(g->gates);
     free_mc(g);
     delete g;
     return MQ3D_OK;
@@ -260,6 +261,19 @@ extern "C" int mq3d_grid_set_partition(mq3d_grid *g, int rank, int world, int ti
     g->part.rank = rank;
     g->part.world = world;
     g->part.tile_shift = shift;
+    return MQ3D_OK;
+}
+
+extern "C" int mq3d_grid_set_batch_gates(mq3d_grid *g, const void *const *events, int n_events) {
+    MQ3D_REQUIRE(g && n_events >= 0 && (n_events == 0 || events), "bad gate list");
+    free(g->gates);
+    g->gates = nullptr;
+    g->n_gates = 0;
+    if (n_events == 0) return MQ3D_OK;
+    g->gates = (void **)malloc(sizeof(void *) * (size_t)n_events);
+    MQ3D_REQUIRE(g->gates != nullptr, "out of host memory");
+    memcpy(g->gates, events, sizeof(void *) * (size_t)n_events);
+    g->n_gates = n_events;
     return MQ3D_OK;
 }
 

@@ -6,6 +6,7 @@ boil down to once the frames are in memory: H2D copy of the raw Quest depth (and
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -38,7 +39,7 @@ def pin(a: np.ndarray) -> torch.Tensor:
 def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K, E_wc, params: IntegrationParams,
                      conf: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
                      has_conf: Optional[torch.Tensor] = None, colors_host: Optional[torch.Tensor] = None,
-                     Kc=None, shard: Optional[tuple] = None) -> SequenceStats:
+                     Kc=None, shard: Optional[tuple] = None, gated: Optional[bool] = None) -> SequenceStats:
     """Integrate [F,H,W] raw NDC depth frames (host, ideally pinned) into `vbg`.
 
     conf/count (float64 / int32 [F,H,W], host or device) enable the reference's confidence mask
@@ -49,7 +50,13 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
 
     shard=(rank, world): multi-GPU upload.  Every rank integrates every frame into its own blocks, but each
     rank moves only 1/world of each chunk over its PCIe link and the chunk is completed by an NCCL
-    all-gather over NVLink (the frame broadcast of SURVEY 8e, sharded), still on the copy stream."""
+    all-gather over NVLink (the frame broadcast of SURVEY 8e, sharded), still on the copy stream.
+
+    gated (default: when the linear depth of the whole sequence fits a quarter of the free device memory): the copy
+    stream uploads every chunk AND runs K1 on it (into one whole-sequence buffer), recording one event per chunk;
+    the fused K2/K3 path is then ONE call whose batches wait for those events on the device
+    (mq3d_grid_set_batch_gates) -- no host synchronisation per chunk, so the device never idles while Python
+    enqueues the next chunk.  gated=False keeps one call per chunk (memory bounded by two chunks)."""
     dev = vbg.device
     F, H, W = (int(x) for x in raw_host.shape)
     if shard is not None and int(shard[1]) > 1:
@@ -80,6 +87,15 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     # runs K1 + fused K2/K3 on chunk k; one event per chunk orders the two streams.
     main = torch.cuda.current_stream(dev)
     copy = _copy_stream(dev)
+    if gated is None and os.environ.get("MQ3D_E2E_GATED") in ("0", "1"):      # A/B switch for measurements
+        gated = os.environ["MQ3D_E2E_GATED"] == "1"
+    if gated is None:
+        with torch.cuda.device(dev):
+            free_b, _ = torch.cuda.mem_get_info()
+        gated = F * H * W * 4 * (2 if use_color else 1) <= free_b // 4
+    if gated:
+        return _integrate_frames_gated(vbg, raw_host, nears, fars, K, E_wc, params, conf, count, has_conf, colors_host,
+                                       Kc, shard, upload, mask, use_color, chunk, main, copy)
     copy.wait_stream(main)
     staged = []
     for f0 in range(0, F, chunk):
@@ -129,6 +145,55 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
                                   total.integrate_ms + st.integrate_ms,
                                   total.slow_div_batches + st.slow_div_batches)
     return total
+
+
+def _integrate_frames_gated(vbg, raw_host, nears, fars, K, E_wc, params, conf, count, has_conf, colors_host, Kc, shard,
+                            upload, mask, use_color, chunk, main, copy) -> SequenceStats:
+    """Copy stream: upload + K1 (+ colour resampling) per chunk into whole-sequence buffers, one event per chunk;
+    compute stream: one fused K2/K3 call gated by those events."""
+    dev = vbg.device
+    F, H, W = (int(x) for x in raw_host.shape)
+    lin = torch.empty((F, H, W), dtype=torch.float32, device=dev)
+    valid = torch.empty((F,), dtype=torch.int32, device=dev)
+    rgbx = torch.empty((F, H, W), dtype=torch.int32, device=dev) if use_color else None
+    for t in (lin, valid, rgbx):
+        if t is not None:
+            t.record_stream(copy)
+    copy.wait_stream(main)          # the buffers above are allocated on the compute stream's pool
+    Kc_np = np.asarray(Kc) if use_color else None
+    sharded = shard is not None and int(shard[1]) > 1
+    events = []
+    for f0 in range(0, F, chunk):
+        f1 = min(F, f0 + chunk)
+        with torch.cuda.stream(copy):
+            raw = upload(raw_host, f0, f1)
+            cpart = upload(conf, f0, f1) if mask and conf.device.type == "cpu" else (conf[f0:f1].to(dev) if mask else None)
+            npart = upload(count, f0, f1) if mask and count.device.type == "cpu" else (count[f0:f1].to(dev) if mask else None)
+            depth_prepare(raw, nears[f0:f1], fars[f0:f1], cpart, npart,
+                          None if (has_conf is None or not mask) else has_conf[f0:f1],
+                          params.confidence_threshold, params.valid_count_threshold, out=lin[f0:f1], valid_out=valid[f0:f1])
+            if use_color:
+                pinned = colors_host.device.type == "cpu" and colors_host.is_pinned()
+                if pinned and sharded:
+                    import torch.distributed as dist
+                    s_rank, s_world = int(shard[0]), int(shard[1])
+                    per = -(-(f1 - f0) // s_world)
+                    full = torch.empty((per * s_world, H, W), dtype=torch.int32, device=dev)
+                    a = min(f1, f0 + s_rank * per)
+                    b = min(f1, a + per)
+                    mine = full[s_rank * per:(s_rank + 1) * per]
+                    if b > a:
+                        color_resample(colors_host[a:b], K[a:b], Kc_np[a:b], W, H, device=dev, out=mine[: b - a])
+                    dist.all_gather_into_tensor(full, mine)
+                    rgbx[f0:f1].copy_(full[: f1 - f0])
+                else:
+                    src = colors_host[f0:f1] if pinned else upload(colors_host, f0, f1)
+                    color_resample(src.contiguous(), K[f0:f1], Kc_np[f0:f1], W, H, device=dev, out=rgbx[f0:f1])
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        events.append(ev)
+    return vbg.integrate_sequence(lin, K, E_wc, params.depth_max, params.trunc_voxel_multiplier, 1.0, frame_valid=valid,
+                                  colors_rgbx=rgbx, batch_frames=chunk, batch_events=events)
 
 
 _COPY_STREAMS: dict = {}

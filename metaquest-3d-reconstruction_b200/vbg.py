@@ -294,8 +294,12 @@ class VoxelBlockGrid:
                            trunc_voxel_multiplier: float, depth_scale: float = 1.0,
                            frame_valid: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
                            color_intrinsics=None, batch_frames: int = 64,
-                           colors_rgbx: Optional[torch.Tensor] = None) -> SequenceStats:
+                           colors_rgbx: Optional[torch.Tensor] = None, batch_events=None) -> SequenceStats:
         """Fused frame loop of ``integrate()`` (o3d_utils.py:231-236) over [F,H,W] linear depth.
+
+        batch_events: one torch.cuda.Event (or None) per batch of `batch_frames` frames; the call waits for event i
+        on the device before it enqueues batch i, so the frames of later batches may still be in flight on another
+        stream (upload + depth_prepare) when the call is made (mq3d_grid_set_batch_gates).
 
         colors: uint8 [F,CH,CW,3], a CUDA tensor or a *pinned* CPU tensor (read in place over PCIe: only the
         W x H sampled pixels per frame travel); other CPU tensors are copied to the device first.
@@ -311,6 +315,9 @@ class VoxelBlockGrid:
             fv = frame_valid.to(self.device).to(torch.int32).contiguous()
         col, Kc, CW, CH = None, Kd, 0, 0
         st = _lib.SeqStats()
+        if batch_events is not None:
+            handles = (C.c_void_p * len(batch_events))(*[None if e is None else e.cuda_event for e in batch_events])
+            _lib.check(_lib.lib().mq3d_grid_set_batch_gates(self._h, handles, len(batch_events)))
         if colors_rgbx is not None and self.has_color:
             if (colors_rgbx.dtype != torch.int32 or tuple(colors_rgbx.shape) != (F, H, W) or not colors_rgbx.is_cuda
                     or not colors_rgbx.is_contiguous()):
@@ -510,16 +517,25 @@ def color_resample(colors: torch.Tensor, depth_intrinsics, color_intrinsics, wid
 
 def depth_prepare(raw: torch.Tensor, nears, fars, conf: Optional[torch.Tensor] = None,
                   count: Optional[torch.Tensor] = None, has_conf: Optional[torch.Tensor] = None,
-                  confidence_threshold: float = 0.0, valid_count_threshold: int = 0):
-    """K1 over [F,H,W] raw NDC depth: returns (linear float32 [F,H,W], frame_valid int32 [F])."""
+                  confidence_threshold: float = 0.0, valid_count_threshold: int = 0,
+                  out: Optional[torch.Tensor] = None, valid_out: Optional[torch.Tensor] = None):
+    """K1 over [F,H,W] raw NDC depth: returns (linear float32 [F,H,W], frame_valid int32 [F]).  out / valid_out:
+    contiguous destination tensors of those shapes (e.g. slices of a whole-sequence buffer)."""
     if raw.dim() != 3 or raw.dtype != torch.float32 or not raw.is_cuda:
         raise RuntimeError("raw must be a float32 CUDA tensor [F,H,W]")
     raw = raw.contiguous()
     F, H, W = raw.shape
     near = _as_np(nears, np.float64, (F,))
     far = _as_np(fars, np.float64, (F,))
-    out = torch.empty_like(raw)
-    valid = torch.empty((F,), dtype=torch.int32, device=raw.device)
+    if out is None:
+        out = torch.empty_like(raw)
+    elif (out.dtype != torch.float32 or tuple(out.shape) != (F, H, W) or out.device != raw.device
+          or not out.is_contiguous()):
+        raise RuntimeError("out must be a contiguous float32 tensor [F,H,W] on the device of raw")
+    valid = valid_out if valid_out is not None else torch.empty((F,), dtype=torch.int32, device=raw.device)
+    if (valid.dtype != torch.int32 or tuple(valid.shape) != (F,) or valid.device != raw.device
+            or not valid.is_contiguous()):
+        raise RuntimeError("valid_out must be a contiguous int32 tensor [F] on the device of raw")
     if conf is not None:
         conf = conf.to(raw.device).to(torch.float64).contiguous()
         count = count.to(raw.device).to(torch.int32).contiguous()

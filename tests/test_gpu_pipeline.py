@@ -133,9 +133,11 @@ def test_compat_layer_runs_the_reference_frame_loop(cuda_device, oracle):
         o3d.t.geometry.VoxelBlockGrid(voxel_size=0.02, block_count=10, device=o3d.core.Device("CPU:0"))
 
 
-def test_integrate_frames_host_pipeline_matches_direct(cuda_device, oracle):
+@pytest.mark.parametrize("gated", [True, False])
+def test_integrate_frames_host_pipeline_matches_direct(cuda_device, oracle, gated):
     """The chunked H2D/compute pipeline (public host-buffer API used by bench.py's e2e number) gives the
-    same grid as one fused call on device-resident frames."""
+    same grid as one fused call on device-resident frames -- both as one call per chunk and as ONE call whose
+    batches are gated on the device by the copy stream's events (upload + K1 + colour resampling per chunk)."""
     import mq3d_b200  # noqa: F401
     from helpers import capture
     from mq3d_b200 import synth
@@ -155,7 +157,7 @@ def test_integrate_frames_host_pipeline_matches_direct(cuda_device, oracle):
     p = IntegrationParams(voxel_size=0.02, depth_max=4.0, trunc_voxel_multiplier=10.0, confidence_threshold=0.3,
                           valid_count_threshold=2, batch_frames=4)
     st = integrate_frames(a, pin(cap.raw), ds.nears, ds.fars, K, Ewc, p, conf=pin(conf), count=pin(count),
-                          colors_host=pin(colors), Kc=Kc)
+                          colors_host=pin(colors), Kc=Kc, gated=gated)
     b = VoxelBlockGrid(attr_names=names, voxel_size=0.02, block_count=300, device=cuda_device)
     lin, valid = depth_prepare(torch.from_numpy(cap.raw).to(cuda_device), ds.nears, ds.fars,
                                torch.from_numpy(conf).to(cuda_device), torch.from_numpy(count).to(cuda_device), None, 0.3, 2)

@@ -17,6 +17,7 @@ def main():
     cfg = dict(bench.WORKLOADS[bench.DEFAULT_WORKLOAD])
     if len(sys.argv) > 1:
         cfg["frames"] = int(sys.argv[1])
+    gated = None if len(sys.argv) <= 2 else bool(int(sys.argv[2]))
     dev = torch.device("cuda", 0)
     wl = bench.build_workload(cfg, dev, 0, 1)
     vbg = VoxelBlockGrid(voxel_size=cfg["voxel"], block_count=cfg["block_count"], device=dev)
@@ -32,7 +33,7 @@ def main():
         t0 = sync()
         vbg.reset()
         t1 = sync()
-        st = integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params)
+        st = integrate_frames(vbg, raw_host, wl["nears"], wl["fars"], wl["K"], wl["Ewc"], params, gated=gated)
         t2 = sync()
         out = vbg.extract_triangle_mesh_arrays(cfg["weight_thr"])
         t3 = sync()
