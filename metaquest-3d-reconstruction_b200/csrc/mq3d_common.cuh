@@ -229,6 +229,8 @@ struct mq3d_grid {
     int64_t rgbx_px;
     float *depth_scratch;   // frames / depth_scale when depth_scale != 1
     int64_t depth_scratch_size;
+    float *dsan;            // one batch of depth frames with every pixel the integrator rejects replaced by -inf (k_touch)
+    int64_t dsan_px;
     // validated fast division by the truncation constant
     float div_checked_trunc;
     int div_fast_ok;

@@ -218,6 +218,7 @@ extern "C" int mq3d_grid_destroy(mq3d_grid *g) {
     cudaFree(g->slot_list);
     cudaFree(g->slot_sorted);
     cudaFree(g->depth_scratch);
+    cudaFree(g->dsan);
     cudaFree(g->rgbx);
     cudaFree(g->frame_params_dev);
     cudaFree(g->seq_dev);

@@ -210,6 +210,35 @@ def test_tiny_depth_takes_the_guarded_division(cuda_device, oracle, pixel):
     assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
 
 
+@pytest.mark.parametrize("variant", ["0", "40"])
+def test_rejected_depth_values_match_the_oracle(cuda_device, oracle, variant, monkeypatch):
+    """Depth pixels the integrator rejects by value -- 0, -0.0, negative, above depth_max, +inf, -inf -- and the ones it
+    keeps -- exactly depth_max, NaN (Open3D's compares let NaN through: tsdf and weight of the voxels that project
+    there follow the oracle).  The default (packed) body sees them through the sanitised
+    batch copy written by k_touch (-inf => `sdf < -trunc`); variant 40 is the scalar body with the four explicit tests."""
+    from mq3d_b200.vbg import VoxelBlockGrid
+    monkeypatch.setenv("MQ3D_INTEG_VARIANT", variant)
+    cap = capture(8)
+    K, Ewc, _ = pipeline_cameras(cap.dataset)
+    lin = _linear(oracle, cap)
+    rng = np.random.default_rng(11)
+    specials = np.array([0.0, -0.0, -1.5, DEPTH_MAX, np.nextafter(np.float32(DEPTH_MAX), np.float32(10.0)), 17.0, np.inf,
+                         -np.inf, np.nan], np.float32)
+    for f in range(len(lin)):
+        ys, xs = rng.integers(0, lin.shape[1], 600), rng.integers(0, lin.shape[2], 600)
+        lin[f, ys, xs] = specials[rng.integers(0, len(specials), 600)]
+    og = oracle.Grid(0.02)
+    oracle_integrate_sequence(oracle, og, lin, K, Ewc, DEPTH_MAX, TRUNC)
+    vbg = VoxelBlockGrid(voxel_size=0.02, block_count=2000, device=cuda_device)
+    vbg.integrate_sequence(torch.from_numpy(lin).to(cuda_device), K, Ewc, DEPTH_MAX, TRUNC, batch_frames=3)
+    k0, t0, w0 = sort_blocks(*oracle_export(og))
+    k1, t1, w1 = sort_blocks(*[x.cpu().numpy() for x in vbg.export_blocks()[:3]])
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    nan0, nan1 = np.isnan(t0), np.isnan(t1)
+    assert np.array_equal(nan0, nan1)          # (Open3D's min(sdf, trunc) turns a NaN sdf into +trunc: usually no NaN survives)
+    assert np.array_equal(t0[~nan0].view(np.uint32), t1[~nan1].view(np.uint32))
+
+
 def test_sequence_resumes_after_mid_sequence_growth(cuda_device, oracle):
     """All batches of a call are enqueued without host synchronisation; a batch whose touch overflows the pool or
     the hash table stops the device-side pipeline, the host grows the grid and resumes from that batch.  Start so
