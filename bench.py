@@ -479,9 +479,11 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "traffic": profile_figure("integrate_traffic", args.workload),
-                     "limiter": "instruction issue (not HBM): a block stays resident in registers for a whole batch "
-                                "of frames, so DRAM moves one load + store per block residency",
+                     "limiter": "FP32 pipe and instruction issue (not HBM): a block stays resident in registers for a "
+                                "whole batch of frames, so DRAM moves one load + store per block residency; the "
+                                "packed-FP32 body keeps the FMA pipe busy ~70 % of the cycles at ~76 % issue-slot use",
                      "issue_slot_frac": profile_figure("integrate_issue", args.workload),
+                     "fma_pipe_frac": profile_figure("integrate_fma", args.workload),
                      "algorithmic_bytes": "batched: bytes_per_voxel x 4096 x block residencies + frame images read "
                                           "once + 12 B keys per residency",
                      "bytes_per_voxel": bytes_per_visit, "block_residencies": loaded, "block_visits": visits_blocks,

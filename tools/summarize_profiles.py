@@ -8,6 +8,7 @@
 number in profiles/<name>.json under <workload> (bench.py reads integrate_traffic / integrate_issue / mc_traffic):
   *_traffic : dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the matching launches)
   *_issue   : smsp__issue_active.avg.pct_of_peak_sustained_active / 100
+  *_fma     : sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active / 100 (FP32 pipe busy cycles)
 """
 import collections
 import csv
@@ -96,6 +97,8 @@ def full(tag, rep, title, figures):
                             float(d["dram__bytes_write.sum"]) * CONV[u["dram__bytes_write.sum"]])
             elif name.endswith("issue"):
                 vals.append(float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]) / 100.0)
+            elif name.endswith("fma"):
+                vals.append(float(d["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]) / 100.0)
         if not vals:
             print(f"no launch matches {rx} for {name}")
             continue
