@@ -113,6 +113,8 @@ def main():
     out["k4_count"] = np.stack(counts)
     assert out["k4_conf"].dtype == np.float64 and out["k4_count"].dtype == np.int32
     assert out["k1_linear"].dtype == np.float32 and out["k4_err"].dtype == np.float32
+    # the float64 promotion in convert_depth_to_linear depends on NumPy's scalar promotion rules (NEP 50, NumPy >= 2)
+    out["meta_numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(HERE, "reference_k1_k4.npz"), **out)
     print({k: (v.shape, str(v.dtype)) for k, v in out.items()})
 
