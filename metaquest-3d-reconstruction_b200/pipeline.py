@@ -52,7 +52,7 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     rank moves only 1/world of each chunk over its PCIe link and the chunk is completed by an NCCL
     all-gather over NVLink (the frame broadcast of SURVEY 8e, sharded), still on the copy stream.
 
-    gated (default: when the linear depth of the whole sequence fits a quarter of the free device memory): the copy
+    gated (default: single-GPU uploads whose whole-sequence linear depth fits a quarter of the free device memory): the copy
     stream uploads every chunk AND runs K1 on it (into one whole-sequence buffer), recording one event per chunk;
     the fused K2/K3 path is then ONE call whose batches wait for those events on the device
     (mq3d_grid_set_batch_gates) -- no host synchronisation per chunk, so the device never idles while Python
@@ -90,9 +90,12 @@ def integrate_frames(vbg: VoxelBlockGrid, raw_host: torch.Tensor, nears, fars, K
     if gated is None and os.environ.get("MQ3D_E2E_GATED") in ("0", "1"):      # A/B switch for measurements
         gated = os.environ["MQ3D_E2E_GATED"] == "1"
     if gated is None:
+        # (sharded uploads keep one call per chunk: with the NCCL all-gather AND K1 of every chunk queued behind the
+        # persistent integrate kernels of all ranks the gated form was no faster at N = 2 and noisier at N = 8)
         with torch.cuda.device(dev):
             free_b, _ = torch.cuda.mem_get_info()
-        gated = F * H * W * 4 * (2 if use_color else 1) <= free_b // 4
+        sharded_upload = shard is not None and int(shard[1]) > 1
+        gated = (not sharded_upload) and F * H * W * 4 * (2 if use_color else 1) <= free_b // 4
     if gated:
         return _integrate_frames_gated(vbg, raw_host, nears, fars, K, E_wc, params, conf, count, has_conf, colors_host,
                                        Kc, shard, upload, mask, use_color, chunk, main, copy)
