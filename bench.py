@@ -500,11 +500,12 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "ms_each_step_rank0": e2e_each,
                 "h2d_note": h2d_note},
         # per step on each rank: reset fill (1) + K1 prepare / finalize (2) + per batch [colour resample, one launch per
-        # 64 frames] + touch + list + sort + integrate launches (unguarded / guarded division x, depth-only, the two
-        # shapes chosen on the device by batch size: all but one return at once) + bitmap clear; MC neighbours / rows /
+        # 64 frames] + touch + list + sort + integrate launches (unguarded / guarded division x, depth-only on a
+        # partitioned grid, the two shapes chosen on the device by batch size: all but one return at once) + bitmap
+        # clear; MC neighbours / rows /
         # classify / scan x 2 / emit [+ colours]
-        "gpu_launches": int(args.steps * (3 + st.batches * ((4 + 2 + -(-min(args.batch, n) // 64)) if color else (4 + 4))
-                                          + (7 if color else 6))),
+        "gpu_launches": int(args.steps * (3 + st.batches * ((4 + 2 + -(-min(args.batch, n) // 64)) if color else
+                                                            (4 + (4 if sharded else 2))) + (7 if color else 6))),
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
