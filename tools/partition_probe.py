@@ -25,14 +25,20 @@ def main():
         os.environ["MQ3D_INTEG_VARIANT"] = v
         vbg = VoxelBlockGrid(voxel_size=cfg["voxel"], block_count=cfg["block_count"], device=dev)
         vbg.set_partition(0, world, 1, integrate_ghosts=False)
-        ms = []
+        ms, tot = [], []
         for _ in range(3):
             vbg.reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             st = vbg.integrate_sequence(lin, wl["K"], wl["Ewc"], cfg["depth_max"], cfg["trunc"], 1.0, frame_valid=valid,
                                         batch_frames=256)
+            e1.record()
+            torch.cuda.synchronize()
             ms.append(st.integrate_ms)
-        print(f"world {world} variant {v}: k_integrate {min(ms):.3f} ms, {st.num_blocks} blocks, "
-              f"{st.block_visits} block visits, {st.blocks_loaded} residencies", file=sys.stderr)
+            tot.append(e0.elapsed_time(e1))
+        print(f"world {world} variant {v}: k_integrate {min(ms):.3f} ms, whole sequence call {min(tot):.3f} ms, touch "
+              f"{st.touch_ms:.3f} ms, {st.num_blocks} blocks, {st.block_visits} block visits, {st.blocks_loaded} residencies",
+              file=sys.stderr)
         vbg.close()
 
 
