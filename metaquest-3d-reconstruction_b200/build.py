@@ -48,7 +48,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _mtime(obj) < max(_mtime(src), hdr_time):
-            cmd = [nvcc] + NVCC_FLAGS + (["-ccbin", ccbin] if ccbin else []) + ["-c", src, "-o", obj]
+            extra = os.environ.get("MQ3D_NVCC_EXTRA", "").split()          # experiments, e.g. -DMQ3D_TWO_PHASE
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-ccbin", ccbin] if ccbin else []) + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             procs.append((s, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
